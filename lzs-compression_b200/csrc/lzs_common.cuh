@@ -1,0 +1,64 @@
+/*
+ * lzs_common.cuh -- LZS format constants and small device helpers shared by the
+ * sm_100a kernels.  Constants restate c/src/liblzs/lzs-common.h:38-53,
+ * lzs.h:57-81 and lzs-compression.c:62 of the reference.
+ *
+ * The same source compiles under the CPU emulator used by the non-GPU tests
+ * (tests/simt/simt.h, -DLZS_SIMT_EMU); the product build is nvcc only.
+ */
+#ifndef LZS_B200_COMMON_CUH
+#define LZS_B200_COMMON_CUH
+
+#include <stdint.h>
+
+#ifdef LZS_SIMT_EMU
+#include "simt.h"
+#define LZS_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(simt::dyn_smem())
+#define LZS_SPIN_HINT() simt_yield()
+#else
+#include <cuda_runtime.h>
+#define LZS_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define LZS_SPIN_HINT() __nanosleep(20)
+#endif
+
+#define LZS_FULL_MASK 0xFFFFFFFFu
+
+namespace lzs {
+
+constexpr uint32_t kWindow = 2047;        /* LZS_MAX_HISTORY_SIZE, lzs.h:60            */
+constexpr uint32_t kSearchMax = 12;       /* LZS_SEARCH_MATCH_MAX, lzs-compression.c:62 */
+constexpr uint32_t kMinLen = 2;           /* MIN_LENGTH, lzs-common.h:51               */
+constexpr uint32_t kMaxShortLen = 8;      /* MAX_SHORT_LENGTH, lzs-common.h:52         */
+constexpr uint32_t kMaxExtLen = 15;       /* MAX_EXTENDED_LENGTH, lzs-common.h:53      */
+constexpr uint32_t kShortOffMax = 127;    /* SHORT_OFFSET_MAX, lzs-common.h:43         */
+
+/* Per-position match record written by K1 and read by K2: (len << 11) | offset,
+ * len in 0 or 2..12 (capped at LZS_SEARCH_MATCH_MAX), offset in 1..2047. */
+typedef uint16_t match_t;
+constexpr uint32_t kMatchOffBits = 11;
+
+__device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+/* Byte swap: the stream is MSB-first, the GPU is little endian. */
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+/* Four bytes starting at byte address `p` (any alignment), built from aligned
+ * 32-bit loads only.  Words that lie entirely at or beyond `end` are not touched
+ * and read as zero, so nothing outside the buffer's own aligned words is read. */
+__device__ __forceinline__ uint32_t load4_unaligned(const uint8_t *p, const uint8_t *end)
+{
+    uintptr_t       a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+    uint32_t        sh = static_cast<uint32_t>(a & 3u) * 8u;
+    uint32_t        lo = 0, hi = 0;
+    if (reinterpret_cast<const uint8_t *>(w) < end) lo = __ldg(w);
+    if (sh != 0 && reinterpret_cast<const uint8_t *>(w + 1) < end) hi = __ldg(w + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+
+}  // namespace lzs
+
+#endif /* LZS_B200_COMMON_CUH */

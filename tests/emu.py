@@ -1,0 +1,106 @@
+"""ctypes front end of tests/simt/libemu.so: the product's kernel sources run on the
+CPU SIMT emulator.  Test infrastructure only (there is no GPU in the build container)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from helpers import ROOT, c_u8p, c_u16p, c_u32p, c_u64p, _ptr
+
+SIMT_DIR = os.path.join(ROOT, "tests", "simt")
+EMU_SO = os.path.join(SIMT_DIR, "libemu.so")
+CSRC = os.path.join(ROOT, "lzs-compression_b200", "csrc")
+
+_lib = None
+
+
+def _needs_build():
+    if not os.path.exists(EMU_SO):
+        return True
+    t = os.path.getmtime(EMU_SO)
+    srcs = [os.path.join(SIMT_DIR, f) for f in os.listdir(SIMT_DIR) if f.endswith((".cpp", ".h"))]
+    srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if _needs_build():
+            subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I" + SIMT_DIR, "-o", EMU_SO,
+                            os.path.join(SIMT_DIR, "emu_kernels.cpp"), os.path.join(SIMT_DIR, "simt.cpp")],
+                           check=True)
+        _lib = ctypes.CDLL(EMU_SO)
+        _lib.emu_decode.argtypes = [c_u8p, c_u64p, c_u32p, c_u8p, c_u64p, c_u32p, c_u32p, ctypes.c_uint32,
+                                    ctypes.c_int, ctypes.c_uint]
+        _lib.emu_match.argtypes = [c_u8p, c_u64p, c_u32p, c_u16p, ctypes.c_uint32, ctypes.c_uint]
+        _lib.emu_parse_pack.argtypes = [c_u8p, c_u64p, c_u32p, c_u16p, c_u8p, c_u64p, c_u32p, c_u32p,
+                                        ctypes.c_uint32]
+    return _lib
+
+
+def _align(x, a):
+    return (x + a - 1) // a * a
+
+
+def pack_streams(streams, align=16, lead=0):
+    """Lay byte strings out in one buffer; returns (buf, off, len). `lead` shifts every
+    stream by that many bytes to exercise unaligned starts."""
+    offs, pos = [], 0
+    for s in streams:
+        pos = _align(pos, align) + lead
+        offs.append(pos)
+        pos += len(s)
+    buf = np.zeros(_align(pos, 16) + 64, dtype=np.uint8)
+    for o, s in zip(offs, streams):
+        buf[o:o + len(s)] = np.frombuffer(bytes(s), dtype=np.uint8)
+    return buf, np.array(offs, dtype=np.uint64), np.array([len(s) for s in streams], dtype=np.uint32)
+
+
+def _out_layout(caps, out_lead):
+    out_off, pos = [], 0
+    for c in caps:
+        pos = _align(pos, 16) + out_lead
+        out_off.append(pos)
+        pos += c
+    dst = np.full(_align(pos, 16) + 64, 0xEE, dtype=np.uint8)
+    return dst, np.array(out_off, dtype=np.uint64), np.array(caps, dtype=np.uint32)
+
+
+def _collect(dst, out_off, caps, out_len, what):
+    res = []
+    for o, c, l in zip(out_off, caps, out_len):
+        o, l = int(o), int(l)
+        assert l <= c
+        assert (dst[o + l:o + c] == 0xEE).all(), what + " wrote past the bytes it reported"
+        res.append(dst[o:o + l].tobytes())
+    return res
+
+
+def decode(streams, caps, lanes=8, grid=2, align=16, lead=0, out_lead=0):
+    src, in_off, in_len = pack_streams(streams, align, lead)
+    dst, out_off, out_cap = _out_layout(caps, out_lead)
+    out_len = np.zeros(len(streams), dtype=np.uint32)
+    rc = lib().emu_decode(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(dst), _ptr(out_off, c_u64p),
+                          _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams), lanes, grid)
+    assert rc == 0
+    return _collect(dst, out_off, caps, out_len, "decoder")
+
+
+def match(streams, grid=1, align=16, lead=0):
+    src, in_off, in_len = pack_streams(streams, align, lead)
+    m = np.zeros(len(src) + 16, dtype=np.uint16)
+    lib().emu_match(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p), len(streams), grid)
+    return [m[int(o):int(o) + int(l)].copy() for o, l in zip(in_off, in_len)], (src, in_off, in_len, m)
+
+
+def compress(streams, caps=None, grid=1, align=16, lead=0, out_lead=0):
+    _, (src, in_off, in_len, m) = match(streams, grid, align, lead)
+    if caps is None:
+        caps = [len(s) + (len(s) + 7) // 8 + 3 for s in streams]
+    dst, out_off, out_cap = _out_layout(caps, out_lead)
+    out_len = np.zeros(len(streams), dtype=np.uint32)
+    lib().emu_parse_pack(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p), _ptr(dst),
+                         _ptr(out_off, c_u64p), _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams))
+    return _collect(dst, out_off, caps, out_len, "packer")

@@ -1,0 +1,56 @@
+/*
+ * emu_kernels.cpp -- builds the product's kernel sources against the CPU SIMT
+ * emulator (simt.h) and exposes them to the non-GPU tests through ctypes.
+ * TEST INFRASTRUCTURE: this is how kernel logic is checked in a container that
+ * has no GPU; the shipped library never contains or calls any of this.
+ */
+#define LZS_SIMT_EMU 1
+#include "../../lzs-compression_b200/csrc/k1_match.cuh"
+#include "../../lzs-compression_b200/csrc/k23_parse_pack.cuh"
+#include "../../lzs-compression_b200/csrc/k4_decode.cuh"
+
+template <int G>
+static void run_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                       const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
+                       unsigned grid)
+{
+    uint32_t counter = 0;
+    simt::launch(dim3(grid), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<G>(), [&] {
+        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter);
+    });
+}
+
+extern "C" int emu_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                          const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
+                          int lanes_per_stream, unsigned grid)
+{
+    switch (lanes_per_stream) {
+        case 4:  run_decode<4>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
+        case 8:  run_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
+        case 16: run_decode<16>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
+        case 32: run_decode<32>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
+        default: return -1;
+    }
+    return 0;
+}
+
+extern "C" int emu_match(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                         uint16_t *matches, uint32_t n, unsigned grid)
+{
+    uint32_t counter = 0;
+    simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
+        lzs::k1_match(in, in_off, in_len, matches, n, &counter);
+    });
+    return 0;
+}
+
+extern "C" int emu_parse_pack(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                              const uint16_t *matches, uint8_t *out, const uint64_t *out_off,
+                              const uint32_t *out_cap, uint32_t *out_len, uint32_t n)
+{
+    unsigned grid = (n + lzs::kK2Warps - 1) / lzs::kK2Warps;
+    simt::launch(dim3(grid), dim3(lzs::kK2Threads), 0, [&] {
+        lzs::k23_parse_pack(in, in_off, in_len, matches, out, out_off, out_cap, out_len, n);
+    });
+    return 0;
+}

@@ -1,0 +1,334 @@
+/*
+ * simt.h -- a small functional emulator of the CUDA execution model, so the
+ * kernel sources under lzs-compression_b200/csrc/*.cuh can be compiled with g++
+ * and exercised on a machine without a GPU.
+ *
+ * TEST INFRASTRUCTURE ONLY.  It exists because the build container has no GPU:
+ * logic errors in a kernel are found here in seconds instead of on a B200 box.
+ * It is never part of the product and proves nothing about performance or about
+ * races between warps; the -m gpu tests run the real kernels on real hardware.
+ *
+ * Model: one thread block at a time; every CUDA thread is a fibre (ucontext) on
+ * one OS thread; fibres switch only inside warp collectives, __syncthreads() and
+ * simt_yield().  Collectives rendezvous per (warp, member mask), so sub-warp
+ * groups that use their own masks work as on Volta+ independent scheduling.
+ */
+#ifndef LZS_SIMT_H
+#define LZS_SIMT_H
+
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <map>
+#include <vector>
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 v = {a, b, c, d}; return v; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __constant__ static const
+
+namespace simt {
+
+struct Rdv {                        /* one rendezvous per (warp, mask) */
+    uint32_t arrived = 0, departing = 0;
+    uint64_t round = 0;
+    uint64_t vals[32], snap[32];
+};
+
+struct Fiber {
+    ucontext_t ctx;
+    char      *stack = nullptr;
+    bool       done = false;
+    uint3      tid;
+};
+
+struct Block {
+    std::vector<Fiber>                  fibers;
+    std::vector<std::map<uint32_t, Rdv>> rdv;       /* per warp */
+    unsigned  nthreads = 0;
+    unsigned  bar_arrived = 0;
+    uint64_t  bar_round = 0;
+    std::map<int, std::pair<unsigned, uint64_t>> named;   /* id -> (arrived, round) */
+    ucontext_t sched;
+    int        current = -1;
+    std::function<void()> body;
+    std::vector<uint8_t> dyn_smem;
+};
+
+extern Block *g_block;
+extern uint3  g_threadIdx, g_blockIdx;
+extern dim3   g_blockDim, g_gridDim;
+
+inline void yield()
+{
+    Block *b = g_block;
+    swapcontext(&b->fibers[b->current].ctx, &b->sched);
+}
+
+inline unsigned lane_id() { return g_threadIdx.x & 31u; }
+inline unsigned warp_id() { return g_threadIdx.x >> 5; }
+
+/* Exchange one 64-bit value among the lanes of `mask`; returns the snapshot. */
+inline const uint64_t *exchange(uint32_t mask, uint64_t v)
+{
+    Block   *b = g_block;
+    unsigned lane = lane_id();
+    if (!((mask >> lane) & 1u)) {
+        fprintf(stderr, "simt: lane %u calls a collective with mask %08x that excludes it\n", lane, mask);
+        abort();
+    }
+    Rdv &r = b->rdv[warp_id()][mask];
+    while (r.departing != 0) yield();           /* previous round still being read */
+    r.vals[lane] = v;
+    r.arrived |= 1u << lane;
+    if (r.arrived == mask) {
+        memcpy(r.snap, r.vals, sizeof r.snap);
+        r.arrived = 0;
+        r.departing = mask;
+        r.round++;
+    } else {
+        uint64_t my = r.round;
+        while (r.round == my) yield();
+    }
+    return r.snap;
+}
+
+inline void depart(uint32_t mask)
+{
+    Rdv &r = g_block->rdv[warp_id()][mask];
+    r.departing &= ~(1u << lane_id());
+}
+
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &body);
+uint8_t *dyn_smem();
+
+}  // namespace simt
+
+#define threadIdx simt::g_threadIdx
+#define blockIdx simt::g_blockIdx
+#define blockDim simt::g_blockDim
+#define gridDim simt::g_gridDim
+#define warpSize 32
+
+/* ------------------------------------------------------------- collectives */
+
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu)
+{
+    simt::exchange(mask, 0);
+    simt::depart(mask);
+}
+
+static inline void __syncthreads()
+{
+    simt::Block *b = simt::g_block;
+    uint64_t     my = b->bar_round;
+    if (++b->bar_arrived == b->nthreads) {
+        b->bar_arrived = 0;
+        b->bar_round++;
+    } else {
+        while (b->bar_round == my) simt::yield();
+    }
+}
+
+/* bar.sync id, nthreads (named barrier; every participant calls sync) */
+static inline void simt_named_barrier_sync(int id, unsigned nthreads)
+{
+    simt::Block *b = simt::g_block;
+    auto        &e = b->named[id];
+    uint64_t     my = e.second;
+    if (++e.first == nthreads) {
+        e.first = 0;
+        e.second++;
+    } else {
+        while (b->named[id].second == my) simt::yield();
+    }
+}
+
+static inline void simt_yield() { simt::yield(); }
+
+template <typename T>
+static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+{
+    static_assert(sizeof(T) <= 8, "shfl value too wide");
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    const uint64_t *s = simt::exchange(mask, raw);
+    unsigned lane = simt::lane_id();
+    unsigned base = lane & ~(unsigned)(width - 1);
+    unsigned from = base + ((unsigned)src & (unsigned)(width - 1));
+    T out;
+    memcpy(&out, &s[from], sizeof(T));
+    simt::depart(mask);
+    return out;
+}
+
+template <typename T>
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    const uint64_t *s = simt::exchange(mask, raw);
+    unsigned lane = simt::lane_id();
+    unsigned base = lane & ~(unsigned)(width - 1);
+    unsigned from = (lane - base >= delta) ? lane - delta : lane;
+    T out;
+    memcpy(&out, &s[from], sizeof(T));
+    simt::depart(mask);
+    return out;
+}
+
+template <typename T>
+static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    const uint64_t *s = simt::exchange(mask, raw);
+    unsigned lane = simt::lane_id();
+    unsigned base = lane & ~(unsigned)(width - 1);
+    unsigned from = (lane - base + delta < (unsigned)width) ? lane + delta : lane;
+    T out;
+    memcpy(&out, &s[from], sizeof(T));
+    simt::depart(mask);
+    return out;
+}
+
+template <typename T>
+static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32)
+{
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    const uint64_t *s = simt::exchange(mask, raw);
+    unsigned lane = simt::lane_id();
+    unsigned from = lane ^ (unsigned)lanemask;
+    if ((from & ~(unsigned)(width - 1)) != (lane & ~(unsigned)(width - 1))) from = lane;
+    T out;
+    memcpy(&out, &s[from], sizeof(T));
+    simt::depart(mask);
+    return out;
+}
+
+static inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+    const uint64_t *s = simt::exchange(mask, pred ? 1 : 0);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if (((mask >> l) & 1u) && s[l]) r |= 1u << l;
+    simt::depart(mask);
+    return r;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+
+static inline unsigned __match_any_sync(unsigned mask, unsigned v)
+{
+    const uint64_t *s = simt::exchange(mask, v);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if (((mask >> l) & 1u) && (unsigned)s[l] == v) r |= 1u << l;
+    simt::depart(mask);
+    return r;
+}
+
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+    const uint64_t *s = simt::exchange(mask, v);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if ((mask >> l) & 1u) r |= (unsigned)s[l];
+    simt::depart(mask);
+    return r;
+}
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v)
+{
+    const uint64_t *s = simt::exchange(mask, v);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if ((mask >> l) & 1u) r += (unsigned)s[l];
+    simt::depart(mask);
+    return r;
+}
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
+{
+    const uint64_t *s = simt::exchange(mask, v);
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++)
+        if (((mask >> l) & 1u) && (unsigned)s[l] > r) r = (unsigned)s[l];
+    simt::depart(mask);
+    return r;
+}
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
+{
+    const uint64_t *s = simt::exchange(mask, v);
+    unsigned r = 0xFFFFFFFFu;
+    for (unsigned l = 0; l < 32; l++)
+        if (((mask >> l) & 1u) && (unsigned)s[l] < r) r = (unsigned)s[l];
+    simt::depart(mask);
+    return r;
+}
+
+/* ------------------------------------------------ scalar intrinsics, atomics */
+
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __brev(unsigned v)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
+{
+    uint64_t both = ((uint64_t)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned sel = (s >> (4 * i)) & 0xF;
+        unsigned byte = (unsigned)(both >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)
+{
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)(v >> (sh & 31));
+}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)
+{
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)((v << (sh & 31)) >> 32);
+}
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+
+template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+
+#endif /* LZS_SIMT_H */
