@@ -1,0 +1,355 @@
+#!/usr/bin/env python3
+"""bench.py -- LZS compress + decompress throughput on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch: every 64 KiB chunk of a
+1 GiB-per-GPU synthetic corpus is compressed into its own LZS stream (kernels K1 match
+finder, K2+K3 parse/pack) and then decompressed again (K4).  `value` is uncompressed
+GB/s (1e9 B/s) through that round trip with all buffers resident in HBM, summed over
+ranks; `compress_gbs` / `decompress_gbs` / `ratio` break it down.  `e2e` is the same
+round trip through the host-pointer C ABI (lzs_b200_*_batch_host) with pinned host
+buffers, copies inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
+  python bench.py --impl reference ...                          # reference C code on host cores
+
+Multi-GPU: one process per GPU (torchrun); chunks are independent streams, so ranks take
+disjoint chunk ranges and the data path has no collective (weak scaling: 1 GiB per GPU).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "lzs-compression_b200", "python"))
+
+METRIC = "LZS compress+decompress round-trip throughput, uncompressed GB/s (64 KiB chunks)"
+SEED = 0x5EED0000 + 2
+CHUNK = 65536
+CPU_SAMPLE_CHUNKS = 2048         # 128 MiB of the same corpus for the CPU legs
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ CPU legs (oracle side)
+
+def cpu_codec():
+    """The unmodified reference build when it travelled with the repo, else the port."""
+    import helpers
+    ref = helpers.reference()
+    if ref is not None:
+        return ref, "reference"
+    return helpers.oracle(), "port"
+
+
+def cpu_roundtrip(codec, raw, n_chunks, chunk, threads):
+    """Compress then decompress n_chunks chunks of `raw` (numpy uint8, one spare byte at the
+    end) on `threads` host threads; returns (t_compress, t_decompress, compressed_bytes)."""
+    import numpy as np
+    stride = (chunk + (chunk + 7) // 8 + 3 + 15) // 16 * 16
+    idx = np.arange(n_chunks, dtype=np.uint64)
+    in_off, in_len = idx * np.uint64(chunk), np.full(n_chunks, chunk, dtype=np.uint32)
+    c_off, c_cap = idx * np.uint64(stride), np.full(n_chunks, stride, dtype=np.uint32)
+    comp = np.zeros(n_chunks * stride + 16, dtype=np.uint8)
+    dec = np.zeros(n_chunks * chunk + 16, dtype=np.uint8)
+    c_len, t_c = codec.run_streams(False, raw, in_off, in_len, comp, c_off, c_cap, threads)
+    d_len, t_d = codec.run_streams(True, comp, c_off, c_len, dec, in_off, in_len, threads)
+    assert (d_len == in_len).all() and (dec[:n_chunks * chunk] == raw[:n_chunks * chunk]).all()
+    return t_c, t_d, int(c_len.sum())
+
+
+def host_corpus(n_chunks, chunk, first_index):
+    import helpers
+    import numpy as np
+    buf = np.zeros(n_chunks * chunk + 16, dtype=np.uint8)
+    buf[:n_chunks * chunk] = helpers.corpus(helpers.CORPUS_MIXED, n_chunks, chunk, seed=SEED, first_index=first_index)
+    return buf
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    codec, kind = cpu_codec()
+    threads = os.cpu_count() or 1
+    n_chunks = CPU_SAMPLE_CHUNKS
+    raw = host_corpus(n_chunks, CHUNK, 0)
+    times = []
+    comp_bytes = 0
+    for it in range(args.warmup + args.steps):
+        t_c, t_d, comp_bytes = cpu_roundtrip(codec, raw, n_chunks, CHUNK, threads)
+        if it >= args.warmup:
+            times.append((t_c, t_d))
+    nbytes = n_chunks * CHUNK
+    tc = sum(t[0] for t in times) / len(times)
+    td = sum(t[1] for t in times) / len(times)
+    value = nbytes / (tc + td) / 1e9
+    sample = "%d x %d B chunks (%d MiB) of the bench corpus per step, all host threads" % (
+        n_chunks, CHUNK, nbytes >> 20)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tc + td) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(),
+        "compress_gbs": nbytes / tc / 1e9, "decompress_gbs": nbytes / td / 1e9, "ratio": nbytes / comp_bytes,
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config():
+    return {"workload": "1 GiB synthetic mixed corpus (text / binary records / incompressible by chunk) per GPU, "
+                        "split into 64 KiB independent LZS streams; compress then decompress (BASELINE configs[1])",
+            "chunk_bytes": CHUNK, "bytes_per_gpu": 1 << 30, "seed": SEED,
+            "l2_policy": "inputs (1 GiB) larger than L2 (126 MB); no flush needed",
+            "parallelism": "independent chunk ranges per GPU, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import lzs_b200 as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the LZS codec has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    B.lib()
+
+    total = 1 << 30
+    n_chunks = total // CHUNK
+    db = B.DeviceBatch(total, CHUNK, device=dev)
+    db.fill(B.CORPUS_MIXED, SEED, first_index=rank * n_chunks)     # this rank's shard of the corpus
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(ev=None):
+        if ev:
+            ev[0].record()
+        db.match_only()
+        if ev:
+            ev[1].record()
+        db.parse_pack_only()
+        if ev:
+            ev[2].record()
+        db.decompress()
+        if ev:
+            ev[3].record()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = B.lib().lzs_b200_kernel_launches()
+    barrier()
+    for k in range(args.steps):
+        one_step(events[k])
+    barrier()
+    launches = B.lib().lzs_b200_kernel_launches() - launches0
+    clocks = sampler.stop()
+
+    t_k1 = sum(e[0].elapsed_time(e[1]) for e in events) / args.steps
+    t_k23 = sum(e[1].elapsed_time(e[2]) for e in events) / args.steps
+    t_k4 = sum(e[2].elapsed_time(e[3]) for e in events) / args.steps
+    t_total = events[0][0].elapsed_time(events[-1][3]) / args.steps       # ms per step, device clock
+    assert db.roundtrip_ok(), "round trip mismatch inside the timed region"
+    comp_bytes = db.compressed_bytes()
+
+    # ---- end to end through the host-pointer C ABI, pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(B, db, total, n_chunks, max(1, min(args.steps, 3)), barrier)
+
+    stats = torch.tensor([t_total, t_k1, t_k23, t_k4, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(comp_bytes)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    t_total, t_k1, t_k23, t_k4, t_e2e = [float(x) for x in stats.tolist()]
+    comp_all = float(sums.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        job_bytes = float(total) * world
+        alg_bytes_k1 = float(total) + comp_all / world           # n + c per launch, this GPU
+        roof = {"bound": "hbm", "kernel": "k1_match (dominant; followed by k23_parse_pack)",
+                "achieved": alg_bytes_k1 / (t_k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes_k1 / (t_k1 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_k1,
+                "per_kernel_ms": {"k1_match": t_k1, "k23_parse_pack": t_k23, "k4_decode": t_k4},
+                "compress_path_frac": alg_bytes_k1 / ((t_k1 + t_k23) * 1e-3) / 1e9 / peak,
+                "decode_frac": alg_bytes_k1 / (t_k4 * 1e-3) / 1e9 / peak}
+        line = {
+            "metric": METRIC, "value": job_bytes / (t_total * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(),
+            "compress_gbs": job_bytes / ((t_k1 + t_k23) * 1e-3) / 1e9,
+            "decompress_gbs": job_bytes / (t_k4 * 1e-3) / 1e9,
+            "ratio": job_bytes / comp_all,
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
+        }
+        if e2e:
+            line["e2e"] = {"value": job_bytes / (t_e2e * 1e-3) / 1e9, "unit": "GB/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "steps": e2e["steps"], "api": "lzs_b200_compress_batch_host + lzs_b200_decompress_batch_host"}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_leg(db)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(B, db, total, n_chunks, steps, barrier):
+    import numpy as np
+    import torch
+    L = B.lib()
+    stride = db.comp_stride
+    raw = torch.empty(total + 64, dtype=torch.uint8).pin_memory()
+    comp = torch.empty(n_chunks * stride + 64, dtype=torch.uint8).pin_memory()
+    dec = torch.empty(total + 64, dtype=torch.uint8).pin_memory()
+    raw[:total].copy_(db.raw[:total])
+    idx = np.arange(n_chunks, dtype=np.uint64)
+    in_off, in_len = idx * np.uint64(CHUNK), np.full(n_chunks, CHUNK, dtype=np.uint32)
+    c_off, c_cap = idx * np.uint64(stride), np.full(n_chunks, stride, dtype=np.uint32)
+    c_len = np.zeros(n_chunks, dtype=np.uint32)
+    d_len = np.zeros(n_chunks, dtype=np.uint32)
+    u8, u32, u64 = B.u8p, B.u32p, B.u64p
+
+    def p(t):
+        return ctypes.cast(t.data_ptr(), u8)
+
+    def step():
+        B.check(L.lzs_b200_compress_batch_host(p(raw), B._p(in_off, u64), B._p(in_len, u32), total, p(comp),
+                                               B._p(c_off, u64), B._p(c_cap, u32), B._p(c_len, u32),
+                                               n_chunks * stride, n_chunks))
+        B.check(L.lzs_b200_decompress_batch_host(p(comp), B._p(c_off, u64), B._p(c_len, u32), n_chunks * stride,
+                                                 p(dec), B._p(in_off, u64), B._p(in_len, u32), B._p(d_len, u32),
+                                                 total, n_chunks))
+
+    step()                                            # warm-up: allocations inside the library
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    assert torch.equal(dec[:total], raw[:total]), "e2e round trip mismatch"
+    hi = int((c_off + c_len.astype(np.uint64)).max())
+    arrays = n_chunks * 24
+    h2d = total + arrays + n_chunks * stride + arrays      # compress input + decompress input span
+    d2h = hi + 4 * n_chunks + total + 4 * n_chunks
+    return {"ms": ms, "h2d": int(h2d), "d2h": int(d2h), "steps": steps}
+
+
+def cpu_baseline_leg(db):
+    import numpy as np
+    codec, kind = cpu_codec()
+    threads = os.cpu_count() or 1
+    n = CPU_SAMPLE_CHUNKS
+    raw = np.zeros(n * CHUNK + 16, dtype=np.uint8)
+    raw[:n * CHUNK] = db.raw[:n * CHUNK].cpu().numpy()
+    cpu_roundtrip(codec, raw, min(n, 256), CHUNK, threads)                     # warm
+    t_c, t_d, comp_bytes = cpu_roundtrip(codec, raw, n, CHUNK, threads)
+    t1_c, t1_d, _ = cpu_roundtrip(codec, raw, 128, CHUNK, 1)
+    nbytes = n * CHUNK
+    return {"value": nbytes / (t_c + t_d) / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+            "sample": "first %d chunks (%d MiB) of the timed corpus, one pass, all host threads" % (n, nbytes >> 20),
+            "compress_gbs": nbytes / t_c / 1e9, "decompress_gbs": nbytes / t_d / 1e9, "ratio": nbytes / comp_bytes,
+            "single_thread": {"compress_gbs": 128 * CHUNK / t1_c / 1e9, "decompress_gbs": 128 * CHUNK / t1_d / 1e9,
+                              "sample": "first 128 chunks (8 MiB), 1 thread"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

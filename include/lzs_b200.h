@@ -1,0 +1,113 @@
+/*
+ * lzs_b200.h -- batch C ABI of the B200 LZS codec (extension of lzs.h).
+ *
+ * The reference library has one call per stream on host memory
+ * (c/src/liblzs/lzs.h:218 lzs_compress, :229 lzs_decompress) and leaves batching to
+ * the caller (c/src/utils/lzs-compress.c:82-134 loops over one file).  A GPU needs
+ * thousands of independent streams per launch, so this header adds the batch form
+ * of exactly those two calls: stream s is
+ *      in  + in_off[s],  in_len[s]  bytes   ->   out + out_off[s], at most out_cap[s] bytes
+ * and out_len[s] receives what lzs_compress / lzs_decompress would have returned
+ * for that stream alone (including the truncated-prefix behaviour when out_cap[s]
+ * is too small).  Streams are independent LZS streams, each ended by its own end
+ * marker, byte-identical to the reference's output for the same boundaries.
+ *
+ * Plain C, plain pointers and sizes: bind it from cgo / JNI / ctypes / FFI as is.
+ * All functions return 0 on success and a negative LZS_B200_E* code on failure;
+ * lzs_b200_last_error() describes the last failure of the calling thread.
+ * There is no CPU fallback: without a CUDA device every call fails with
+ * LZS_B200_ENODEVICE.
+ */
+#ifndef LZS_B200_BATCH_H
+#define LZS_B200_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZS_B200_OK         0
+#define LZS_B200_ENODEVICE (-1)   /* no usable CUDA device / driver                     */
+#define LZS_B200_ECUDA     (-2)   /* a CUDA runtime call or kernel failed               */
+#define LZS_B200_EINVAL    (-3)   /* bad argument (null pointer, scratch too small ...) */
+#define LZS_B200_ENOMEM    (-4)   /* device or host allocation failed                   */
+
+/* Offsets handed to the *_device calls should be multiples of this for the
+ * vectorised paths (other alignments work, byte by byte). */
+#define LZS_B200_ALIGN 16u
+
+const char *lzs_b200_last_error(void);
+int         lzs_b200_device_count(void);
+
+/* ------------------------------------------------------------------------------
+ * Device-resident batches.  Every pointer below is a DEVICE pointer on the current
+ * CUDA device; `stream` is a cudaStream_t (NULL = default stream).  Calls enqueue
+ * work and return without synchronising.
+ *
+ * in_span = number of bytes of `in` covered by the batch, i.e. max(in_off+in_len);
+ * the compressor keeps one 16-bit match record per covered input byte in scratch.
+ * ---------------------------------------------------------------------------- */
+size_t lzs_b200_compress_scratch_bytes(uint64_t in_span);
+size_t lzs_b200_decompress_scratch_bytes(void);
+
+/* batch form of lzs_compress (reference lzs.h:218) */
+int lzs_b200_compress_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                   uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                   const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams,
+                                   void *scratch, size_t scratch_bytes, void *stream);
+
+/* batch form of lzs_decompress (reference lzs.h:229) */
+int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                     uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                     uint32_t *out_len, uint32_t n_streams, void *scratch,
+                                     size_t scratch_bytes, void *stream);
+
+/* Individual stages of the compressor, for tests and profiling:
+ * K1 writes one record per input byte, (len << 11) | offset with len 0 or 2..12;
+ * K2+K3 turn records + input into streams. */
+int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream);
+int lzs_b200_parse_pack_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                     const uint16_t *matches, uint8_t *out, const uint64_t *out_off,
+                                     const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams,
+                                     void *stream);
+
+/* ------------------------------------------------------------------------------
+ * Host-resident batches: same meaning, HOST pointers, synchronous.  Input is
+ * copied to the device, processed and copied back inside the call (pinned host
+ * memory makes the copies faster but is not required).  in_span / out_span are the
+ * number of bytes of `in` / `out` covered by the batch.
+ * ---------------------------------------------------------------------------- */
+int lzs_b200_compress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                 uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                 const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
+                                 uint32_t n_streams);
+int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                   uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                   const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
+                                   uint32_t n_streams);
+
+/* Uniform chunking helpers (host arrays): stream s covers [s*chunk, min((s+1)*chunk, total))
+ * and its output slot starts at s*out_stride. */
+uint32_t lzs_b200_chunk_count(uint64_t total, uint32_t chunk);
+void     lzs_b200_chunk_layout(uint64_t total, uint32_t chunk, uint64_t out_stride, uint64_t *in_off,
+                               uint32_t *in_len, uint64_t *out_off, uint32_t *out_cap);
+
+/* Synthetic corpus generated in place on the device:
+ * n streams of stream_len bytes at dst + s*stride, stream index first_index + s. */
+int lzs_b200_corpus_fill_device(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
+                                uint64_t n, uint64_t seed, int kind, void *stream);
+
+/* Tuning knobs (also read once from the environment: LZS_B200_DECODE_LANES). */
+int lzs_b200_set_decode_lanes(int lanes_per_stream);   /* 4, 8, 16 or 32 */
+
+/* Number of kernels launched by this library in the calling process so far. */
+uint64_t lzs_b200_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LZS_B200_BATCH_H */

@@ -1,0 +1,451 @@
+/*
+ * lzs_b200.cu -- the C ABI (include/lzs_b200.h and the single-call part of
+ * include/lzs.h) over the sm_100a kernels K1..K4.
+ *
+ * Host code here is launch plumbing only: argument checks, scratch carving,
+ * stream-ordered launches, host<->device copies for the host-pointer entry points.
+ * All codec work happens in the kernels; there is no CPU implementation behind any
+ * entry point, and a missing device is reported as an error, never papered over.
+ */
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/lzs.h"
+#include "../../include/lzs_b200.h"
+#include "corpus.h"
+#include "k1_match.cuh"
+#include "k23_parse_pack.cuh"
+#include "k4_decode.cuh"
+
+namespace {
+
+thread_local char          g_err[512] = "";
+std::atomic<uint64_t>      g_launches{0};
+std::atomic<int>           g_decode_lanes{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver           \
+                            ? LZS_B200_ENODEVICE : LZS_B200_ECUDA,                             \
+                        "%s failed: %s", #expr, cudaGetErrorString(e_));                       \
+    } while (0)
+
+struct DeviceInfo {
+    int  sms = 0;
+    bool ok = false;
+    int  dec_blocks[4] = {0, 0, 0, 0};   /* resident K4 blocks per SM for G = 4, 8, 16, 32 */
+};
+
+/* per-device one-time setup: opt in to large dynamic shared memory, query occupancy */
+int device_info(DeviceInfo **out)
+{
+    static DeviceInfo info[64];
+    static std::mutex mu;
+    int               dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(LZS_B200_EINVAL, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceInfo &d = info[dev];
+    if (!d.ok) {
+        CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaFuncSetAttribute(lzs::k1_match, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lzs::kK1SmemBytes)));
+        CUDA_TRY(cudaFuncSetAttribute(lzs::k4_decode<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lzs::k4_smem_bytes<4>())));
+        CUDA_TRY(cudaFuncSetAttribute(lzs::k4_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lzs::k4_smem_bytes<8>())));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.dec_blocks[0], lzs::k4_decode<4>,
+                                                               lzs::kDecThreads, lzs::k4_smem_bytes<4>()));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.dec_blocks[1], lzs::k4_decode<8>,
+                                                               lzs::kDecThreads, lzs::k4_smem_bytes<8>()));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.dec_blocks[2], lzs::k4_decode<16>,
+                                                               lzs::kDecThreads, lzs::k4_smem_bytes<16>()));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.dec_blocks[3], lzs::k4_decode<32>,
+                                                               lzs::kDecThreads, lzs::k4_smem_bytes<32>()));
+        d.ok = true;
+    }
+    *out = &d;
+    return LZS_B200_OK;
+}
+
+int decode_lanes()
+{
+    int g = g_decode_lanes.load();
+    if (g == 0) {
+        const char *e = getenv("LZS_B200_DECODE_LANES");
+        g = e ? atoi(e) : 8;
+        if (g != 4 && g != 8 && g != 16 && g != 32) g = 8;
+        g_decode_lanes.store(g);
+    }
+    return g;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr size_t kCounterBytes = 256;    /* work counters live at the start of scratch */
+
+__global__ void corpus_fill_kernel(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
+                                   uint64_t n, uint64_t seed, int kind)
+{
+    const uint64_t s = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s < n) lzs_corpus_fill(dst + s * stride, stream_len, seed, first_index + s, kind);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lzs_b200_last_error(void) { return g_err; }
+
+int lzs_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t lzs_b200_kernel_launches(void) { return g_launches.load(); }
+
+int lzs_b200_set_decode_lanes(int lanes)
+{
+    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return fail(LZS_B200_EINVAL, "decode lanes must be 4, 8, 16 or 32 (got %d)", lanes);
+    g_decode_lanes.store(lanes);
+    return LZS_B200_OK;
+}
+
+size_t lzs_b200_compress_scratch_bytes(uint64_t in_span)
+{
+    return kCounterBytes + align_up(static_cast<size_t>(in_span) * sizeof(lzs::match_t) + 64, 256);
+}
+
+size_t lzs_b200_decompress_scratch_bytes(void) { return kCounterBytes; }
+
+int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!in || !in_off || !in_len || !matches || !counter) return fail(LZS_B200_EINVAL, "null pointer");
+    DeviceInfo *d = nullptr;
+    int         rc = device_info(&d);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    const unsigned grid = n_streams < static_cast<uint32_t>(d->sms) ? n_streams : static_cast<unsigned>(d->sms);
+    lzs::k1_match<<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
+                                                                   counter);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+int lzs_b200_parse_pack_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                     const uint16_t *matches, uint8_t *out, const uint64_t *out_off,
+                                     const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams,
+                                     void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!in || !in_off || !in_len || !matches || !out || !out_off || !out_cap || !out_len)
+        return fail(LZS_B200_EINVAL, "null pointer");
+    cudaStream_t   st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (n_streams + lzs::kK2Warps - 1) / lzs::kK2Warps;
+    lzs::k23_parse_pack<<<grid, lzs::kK2Threads, 0, st>>>(in, in_off, in_len, matches, out, out_off, out_cap,
+                                                          out_len, n_streams);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+int lzs_b200_compress_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                   uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                   const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams,
+                                   void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!scratch || scratch_bytes < lzs_b200_compress_scratch_bytes(in_span))
+        return fail(LZS_B200_EINVAL, "scratch too small: need %zu bytes, got %zu",
+                    lzs_b200_compress_scratch_bytes(in_span), scratch_bytes);
+    uint32_t *counter = static_cast<uint32_t *>(scratch);
+    uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(scratch) + kCounterBytes);
+    int rc = lzs_b200_match_batch_device(in, in_off, in_len, matches, n_streams, counter, stream);
+    if (rc) return rc;
+    return lzs_b200_parse_pack_batch_device(in, in_off, in_len, matches, out, out_off, out_cap, out_len,
+                                            n_streams, stream);
+}
+
+int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                     uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                     uint32_t *out_len, uint32_t n_streams, void *scratch,
+                                     size_t scratch_bytes, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len)
+        return fail(LZS_B200_EINVAL, "null pointer");
+    if (!scratch || scratch_bytes < kCounterBytes) return fail(LZS_B200_EINVAL, "scratch too small");
+    DeviceInfo *d = nullptr;
+    int         rc = device_info(&d);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t    *counter = static_cast<uint32_t *>(scratch);
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    const int lanes = decode_lanes();
+    const int idx = lanes == 4 ? 0 : lanes == 8 ? 1 : lanes == 16 ? 2 : 3;
+    const unsigned per_block = lzs::kDecThreads / lanes;
+    unsigned       want = (n_streams + per_block - 1) / per_block;
+    unsigned       resident = static_cast<unsigned>(d->sms) * static_cast<unsigned>(d->dec_blocks[idx] > 0 ? d->dec_blocks[idx] : 1);
+    const unsigned grid = want < resident ? want : resident;
+    switch (lanes) {
+        case 4:
+            lzs::k4_decode<4><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<4>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+            break;
+        case 16:
+            lzs::k4_decode<16><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<16>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+            break;
+        case 32:
+            lzs::k4_decode<32><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<32>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+            break;
+        default:
+            lzs::k4_decode<8><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<8>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+            break;
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+int lzs_b200_corpus_fill_device(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
+                                uint64_t n, uint64_t seed, int kind, void *stream)
+{
+    if (n == 0) return LZS_B200_OK;
+    if (!dst) return fail(LZS_B200_EINVAL, "null pointer");
+    const unsigned threads = 64;
+    const unsigned grid = static_cast<unsigned>((n + threads - 1) / threads);
+    corpus_fill_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(dst, stride, stream_len,
+                                                                              first_index, n, seed, kind);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+uint32_t lzs_b200_chunk_count(uint64_t total, uint32_t chunk)
+{
+    if (chunk == 0) return 0;
+    return static_cast<uint32_t>((total + chunk - 1) / chunk);
+}
+
+void lzs_b200_chunk_layout(uint64_t total, uint32_t chunk, uint64_t out_stride, uint64_t *in_off,
+                           uint32_t *in_len, uint64_t *out_off, uint32_t *out_cap)
+{
+    const uint32_t n = lzs_b200_chunk_count(total, chunk);
+    for (uint32_t s = 0; s < n; s++) {
+        const uint64_t o = static_cast<uint64_t>(s) * chunk;
+        const uint64_t l = total - o < chunk ? total - o : chunk;
+        if (in_off) in_off[s] = o;
+        if (in_len) in_len[s] = static_cast<uint32_t>(l);
+        if (out_off) out_off[s] = static_cast<uint64_t>(s) * out_stride;
+        if (out_cap) out_cap[s] = static_cast<uint32_t>(out_stride);
+    }
+}
+
+}  // extern "C"
+
+/* ------------------------------------------------------------------ host batches */
+
+namespace {
+
+/* Grow-only device arena for the host-pointer entry points (one per device). */
+struct HostPath {
+    std::mutex   mu;
+    cudaStream_t stream = nullptr;
+    void        *buf[8] = {};
+    size_t       cap[8] = {};
+
+    int reserve(int slot, size_t bytes)
+    {
+        bytes = align_up(bytes ? bytes : 1, 256);
+        if (cap[slot] >= bytes) return LZS_B200_OK;
+        if (buf[slot]) cudaFree(buf[slot]);
+        buf[slot] = nullptr;
+        cap[slot] = 0;
+        cudaError_t e = cudaMalloc(&buf[slot], bytes);
+        if (e != cudaSuccess)
+            return fail(e == cudaErrorNoDevice ? LZS_B200_ENODEVICE : LZS_B200_ENOMEM,
+                        "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap[slot] = bytes;
+        return LZS_B200_OK;
+    }
+};
+
+int host_path(HostPath **out)
+{
+    static HostPath paths[64];
+    int             dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(LZS_B200_EINVAL, "device ordinal %d out of range", dev);
+    HostPath &p = paths[dev];
+    if (!p.stream) {
+        std::lock_guard<std::mutex> lock(p.mu);
+        if (!p.stream) CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    }
+    *out = &p;
+    return LZS_B200_OK;
+}
+
+enum { S_IN, S_OUT, S_INOFF, S_INLEN, S_OUTOFF, S_OUTCAP, S_OUTLEN, S_SCRATCH };
+
+int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                   uint64_t in_span, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                   uint32_t *out_len, uint64_t out_span, uint32_t n)
+{
+    if (n == 0) return LZS_B200_OK;
+    if (!in_off || !in_len || !out_off || !out_cap || !out_len || (!in && in_span) || (!out && out_span))
+        return fail(LZS_B200_EINVAL, "null pointer");
+    if (lzs_b200_device_count() <= 0) return fail(LZS_B200_ENODEVICE, "no CUDA device: the LZS codec has no CPU path");
+    HostPath *hp = nullptr;
+    int       rc = host_path(&hp);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(hp->mu);
+    HostPath    &p = *hp;
+    cudaStream_t st = p.stream;
+    const size_t scratch = decompress ? lzs_b200_decompress_scratch_bytes() : lzs_b200_compress_scratch_bytes(in_span);
+    if ((rc = p.reserve(S_IN, in_span + 64))) return rc;
+    if ((rc = p.reserve(S_OUT, out_span + 64))) return rc;
+    if ((rc = p.reserve(S_INOFF, n * sizeof(uint64_t)))) return rc;
+    if ((rc = p.reserve(S_INLEN, n * sizeof(uint32_t)))) return rc;
+    if ((rc = p.reserve(S_OUTOFF, n * sizeof(uint64_t)))) return rc;
+    if ((rc = p.reserve(S_OUTCAP, n * sizeof(uint32_t)))) return rc;
+    if ((rc = p.reserve(S_OUTLEN, n * sizeof(uint32_t)))) return rc;
+    if ((rc = p.reserve(S_SCRATCH, scratch))) return rc;
+
+    uint8_t *d_in = static_cast<uint8_t *>(p.buf[S_IN]);
+    uint8_t *d_out = static_cast<uint8_t *>(p.buf[S_OUT]);
+    if (in_span) CUDA_TRY(cudaMemcpyAsync(d_in, in, in_span, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p.buf[S_INOFF], in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p.buf[S_INLEN], in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p.buf[S_OUTOFF], out_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p.buf[S_OUTCAP], out_cap, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (decompress)
+        rc = lzs_b200_decompress_batch_device(d_in, static_cast<uint64_t *>(p.buf[S_INOFF]),
+                                              static_cast<uint32_t *>(p.buf[S_INLEN]), d_out,
+                                              static_cast<uint64_t *>(p.buf[S_OUTOFF]),
+                                              static_cast<uint32_t *>(p.buf[S_OUTCAP]),
+                                              static_cast<uint32_t *>(p.buf[S_OUTLEN]), n, p.buf[S_SCRATCH],
+                                              p.cap[S_SCRATCH], st);
+    else
+        rc = lzs_b200_compress_batch_device(d_in, static_cast<uint64_t *>(p.buf[S_INOFF]),
+                                            static_cast<uint32_t *>(p.buf[S_INLEN]), in_span, d_out,
+                                            static_cast<uint64_t *>(p.buf[S_OUTOFF]),
+                                            static_cast<uint32_t *>(p.buf[S_OUTCAP]),
+                                            static_cast<uint32_t *>(p.buf[S_OUTLEN]), n, p.buf[S_SCRATCH],
+                                            p.cap[S_SCRATCH], st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_len, p.buf[S_OUTLEN], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    /* Copy back only what was produced.  Few streams: one copy each; many streams:
+     * one copy of the covered span (the gaps between slots are never read by callers). */
+    if (n <= 8) {
+        for (uint32_t s = 0; s < n; s++)
+            if (out_len[s])
+                CUDA_TRY(cudaMemcpyAsync(out + out_off[s], d_out + out_off[s], out_len[s],
+                                         cudaMemcpyDeviceToHost, st));
+    } else {
+        uint64_t hi = 0;
+        for (uint32_t s = 0; s < n; s++)
+            if (out_len[s] && out_off[s] + out_len[s] > hi) hi = out_off[s] + out_len[s];
+        if (hi) CUDA_TRY(cudaMemcpyAsync(out, d_out, hi, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return LZS_B200_OK;
+}
+
+/* single stream through the host path; loud on failure, 0 bytes as the reference's
+ * only "error" value */
+size_t single_call(bool decompress, uint8_t *out, size_t out_cap, const uint8_t *in, size_t in_len)
+{
+    if (in_len > 0xFFFFFF00ull || out_cap > 0xFFFFFF00ull) {
+        /* the batch ABI uses 32-bit stream lengths; clamp the capacity, refuse huge inputs */
+        if (in_len > 0xFFFFFF00ull) {
+            fprintf(stderr, "lzs (b200): single-call input of %zu bytes exceeds the 4 GiB stream limit\n", in_len);
+            return 0;
+        }
+        out_cap = 0xFFFFFF00ull;
+    }
+    const uint64_t in_off = 0, out_off = 0;
+    const uint32_t ilen = static_cast<uint32_t>(in_len), ocap = static_cast<uint32_t>(out_cap);
+    uint32_t       olen = 0;
+    uint8_t        dummy = 0;
+    int rc = run_host_batch(decompress, in ? in : &dummy, &in_off, &ilen, in_len, out ? out : &dummy, &out_off,
+                            &ocap, &olen, out_cap, 1);
+    if (rc) {
+        fprintf(stderr, "lzs (b200): %s failed (%d): %s\n", decompress ? "lzs_decompress" : "lzs_compress", rc,
+                lzs_b200_last_error());
+        return 0;
+    }
+    return olen;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lzs_b200_compress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                 uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                 const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
+                                 uint32_t n_streams)
+{
+    return run_host_batch(false, in, in_off, in_len, in_span, out, out_off, out_cap, out_len, out_span, n_streams);
+}
+
+int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                   uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                   const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
+                                   uint32_t n_streams)
+{
+    return run_host_batch(true, in, in_off, in_len, in_span, out, out_off, out_cap, out_len, out_span, n_streams);
+}
+
+/* ---- reference single-call entry points (c/src/liblzs/lzs.h:218, :224, :229) ---- */
+
+size_t lzs_compress(uint8_t *a_pOutData, size_t a_outBufferSize, const uint8_t *a_pInData, size_t a_inLen)
+{
+    return single_call(false, a_pOutData, a_outBufferSize, a_pInData, a_inLen);
+}
+
+/* The reference's "simple" variant differs only in how it searches (brute force,
+ * lzs-compression-simple.c:264-278); its output is byte-identical, so it is the same
+ * engine here. */
+size_t lzs_simple_compress(uint8_t *a_pOutData, size_t a_outBufferSize, const uint8_t *a_pInData, size_t a_inLen)
+{
+    return single_call(false, a_pOutData, a_outBufferSize, a_pInData, a_inLen);
+}
+
+size_t lzs_decompress(uint8_t *a_pOutData, size_t a_outBufferSize, const uint8_t *a_pInData, size_t a_inLen)
+{
+    return single_call(true, a_pOutData, a_outBufferSize, a_pInData, a_inLen);
+}
+
+}  // extern "C"

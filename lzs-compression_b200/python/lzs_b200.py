@@ -1,0 +1,245 @@
+"""ctypes binding of liblzs.so (include/lzs.h + include/lzs_b200.h).
+
+This is the thin Python mirror of the C ABI used by the tests and bench.py; it adds
+no codec logic.  The library is built in-tree (lzs-compression_b200/Makefile) and is
+required: if it cannot be loaded, or no CUDA device is present, calls raise -- there
+is no CPU fallback anywhere in this package.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "liblzs.so")
+
+u8p = ctypes.POINTER(ctypes.c_uint8)
+u16p = ctypes.POINTER(ctypes.c_uint16)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+u64p = ctypes.POINTER(ctypes.c_uint64)
+vp = ctypes.c_void_p
+
+ALIGN = 16
+CORPUS_TEXT, CORPUS_BINARY, CORPUS_RANDOM, CORPUS_MIXED, CORPUS_PACKET = range(5)
+
+
+class LzsError(RuntimeError):
+    pass
+
+
+def compressed_max(n):
+    """LZS_COMPRESSED_MAX (include/lzs.h; reference lzs.h:77)."""
+    return n + (n + 7) // 8 + 3
+
+
+def aligned_stride(nbytes, align=ALIGN):
+    return (nbytes + align - 1) // align * align
+
+
+def build(verbose=False):
+    """Compile liblzs.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", PKG_DIR], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise LzsError("building liblzs.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+_DEVICE_BATCH = [vp, vp, vp]          # in, in_off, in_len (device pointers as integers)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LzsError("liblzs.so is not built: run `make -C lzs-compression_b200` "
+                       "(or __graft_entry__.build()); there is no fallback implementation")
+    L = ctypes.CDLL(LIB_PATH)
+    L.lzs_b200_last_error.restype = ctypes.c_char_p
+    L.lzs_b200_device_count.restype = ctypes.c_int
+    L.lzs_b200_kernel_launches.restype = ctypes.c_uint64
+    L.lzs_b200_compress_scratch_bytes.restype = ctypes.c_size_t
+    L.lzs_b200_compress_scratch_bytes.argtypes = [ctypes.c_uint64]
+    L.lzs_b200_decompress_scratch_bytes.restype = ctypes.c_size_t
+    L.lzs_b200_compress_batch_device.argtypes = [vp, vp, vp, ctypes.c_uint64, vp, vp, vp, vp, ctypes.c_uint32,
+                                                 vp, ctypes.c_size_t, vp]
+    L.lzs_b200_decompress_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp,
+                                                   ctypes.c_size_t, vp]
+    L.lzs_b200_match_batch_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, vp, vp]
+    L.lzs_b200_parse_pack_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
+    host = [u8p, u64p, u32p, ctypes.c_uint64, u8p, u64p, u32p, u32p, ctypes.c_uint64, ctypes.c_uint32]
+    L.lzs_b200_compress_batch_host.argtypes = host
+    L.lzs_b200_decompress_batch_host.argtypes = host
+    L.lzs_b200_corpus_fill_device.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
+                                              ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp]
+    L.lzs_b200_set_decode_lanes.argtypes = [ctypes.c_int]
+    L.lzs_b200_chunk_count.restype = ctypes.c_uint32
+    L.lzs_b200_chunk_count.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
+    for name in ("lzs_compress", "lzs_simple_compress", "lzs_decompress"):
+        f = getattr(L, name)
+        f.restype = ctypes.c_size_t
+        f.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise LzsError("liblzs call failed (%d): %s" % (rc, lib().lzs_b200_last_error().decode()))
+
+
+def _p(a, typ=u8p):
+    return a.ctypes.data_as(typ)
+
+
+# ----------------------------------------------------------------- reference-shaped calls
+
+def lzs_compress(data, out_size=None):
+    """lzs_compress(out, outSize, in, inLen) on host bytes (reference lzs.h:218)."""
+    data = bytes(data)
+    n = len(data)
+    cap = compressed_max(n) if out_size is None else out_size
+    src = np.frombuffer(data + b"\0", dtype=np.uint8).copy()
+    dst = np.zeros(max(cap, 1), dtype=np.uint8)
+    r = lib().lzs_compress(_p(dst), cap, _p(src), n)
+    return dst[:r].tobytes()
+
+
+def lzs_simple_compress(data, out_size=None):
+    data = bytes(data)
+    n = len(data)
+    cap = compressed_max(n) if out_size is None else out_size
+    src = np.frombuffer(data + b"\0", dtype=np.uint8).copy()
+    dst = np.zeros(max(cap, 1), dtype=np.uint8)
+    r = lib().lzs_simple_compress(_p(dst), cap, _p(src), n)
+    return dst[:r].tobytes()
+
+
+def lzs_decompress(data, out_size):
+    """lzs_decompress(out, outSize, in, inLen) on host bytes (reference lzs.h:229)."""
+    data = bytes(data)
+    src = np.frombuffer(data + b"\0", dtype=np.uint8).copy()
+    dst = np.zeros(max(out_size, 1), dtype=np.uint8)
+    r = lib().lzs_decompress(_p(dst), out_size, _p(src), len(data))
+    return dst[:r].tobytes()
+
+
+# ------------------------------------------------------------------------ host batches
+
+def layout(lengths, slot=None, align=ALIGN):
+    """Offsets for streams of the given lengths, each slot `slot(len)` bytes, aligned."""
+    lengths = np.asarray(lengths, dtype=np.uint32)
+    slots = lengths.astype(np.uint64) if slot is None else np.array([slot(int(x)) for x in lengths], dtype=np.uint64)
+    strides = (slots + np.uint64(align - 1)) // np.uint64(align) * np.uint64(align)
+    off = np.zeros(len(lengths), dtype=np.uint64)
+    if len(lengths) > 1:
+        off[1:] = np.cumsum(strides[:-1])
+    span = int(off[-1] + slots[-1]) if len(lengths) else 0
+    return off, slots.astype(np.uint32), span
+
+
+def _host_batch(fn, src, in_off, in_len, out_off, out_cap, out_span):
+    n = len(in_len)
+    in_span = int((in_off + in_len.astype(np.uint64)).max()) if n else 0
+    dst = np.zeros(out_span + 64, dtype=np.uint8)
+    out_len = np.zeros(max(n, 1), dtype=np.uint32)
+    check(fn(_p(src), _p(in_off, u64p), _p(in_len, u32p), in_span, _p(dst), _p(out_off, u64p), _p(out_cap, u32p),
+             _p(out_len, u32p), out_span, n))
+    return dst, out_len[:n]
+
+
+def compress_streams(streams, caps=None):
+    """Batch of independent host byte strings -> list of LZS streams (one launch)."""
+    streams = [bytes(s) for s in streams]
+    in_off, in_len, in_span = layout([len(s) for s in streams])
+    src = np.zeros(in_span + 64, dtype=np.uint8)
+    for o, s in zip(in_off, streams):
+        src[int(o):int(o) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    caps = [compressed_max(len(s)) for s in streams] if caps is None else list(caps)
+    out_off, out_cap, out_span = layout(caps)
+    dst, out_len = _host_batch(lib().lzs_b200_compress_batch_host, src, in_off, in_len, out_off, out_cap, out_span)
+    return [dst[int(o):int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+
+
+def decompress_streams(streams, caps):
+    streams = [bytes(s) for s in streams]
+    in_off, in_len, in_span = layout([len(s) for s in streams])
+    src = np.zeros(in_span + 64, dtype=np.uint8)
+    for o, s in zip(in_off, streams):
+        src[int(o):int(o) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    out_off, out_cap, out_span = layout(list(caps))
+    dst, out_len = _host_batch(lib().lzs_b200_decompress_batch_host, src, in_off, in_len, out_off, out_cap, out_span)
+    return [dst[int(o):int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+
+
+# ---------------------------------------------------------------------- device batches
+
+class DeviceBatch:
+    """Device-resident uniform chunking of one torch.uint8 buffer (plumbing only:
+    torch provides the allocations and the stream; all work is in liblzs.so)."""
+
+    def __init__(self, total_bytes, chunk, device="cuda:0"):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.total = int(total_bytes)
+        self.chunk = int(chunk)
+        self.n = (self.total + self.chunk - 1) // self.chunk
+        self.comp_stride = aligned_stride(compressed_max(self.chunk))
+        idx = torch.arange(self.n, dtype=torch.int64, device=self.device)
+        self.raw_off = idx * self.chunk
+        self.raw_len = torch.full((self.n,), self.chunk, dtype=torch.int32, device=self.device)
+        if self.n:
+            self.raw_len[-1] = self.total - (self.n - 1) * self.chunk
+        self.comp_off = idx * self.comp_stride
+        self.comp_cap = torch.full((self.n,), self.comp_stride, dtype=torch.int32, device=self.device)
+        self.comp_len = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        self.dec_len = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        self.raw = torch.empty(self.total + 64, dtype=torch.uint8, device=self.device)
+        self.comp = torch.empty(self.n * self.comp_stride + 64, dtype=torch.uint8, device=self.device)
+        self.dec = torch.empty(self.total + 64, dtype=torch.uint8, device=self.device)
+        nscratch = lib().lzs_b200_compress_scratch_bytes(self.total)
+        self.scratch = torch.empty(nscratch, dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def fill(self, kind, seed, first_index=0):
+        check(lib().lzs_b200_corpus_fill_device(self.raw.data_ptr(), self.chunk, self.chunk, first_index, self.n,
+                                                seed, kind, self._stream()))
+
+    def compress(self):
+        check(lib().lzs_b200_compress_batch_device(
+            self.raw.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(), self.total,
+            self.comp.data_ptr(), self.comp_off.data_ptr(), self.comp_cap.data_ptr(), self.comp_len.data_ptr(),
+            self.n, self.scratch.data_ptr(), self.scratch.numel(), self._stream()))
+
+    def match_only(self):
+        check(lib().lzs_b200_match_batch_device(
+            self.raw.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(),
+            self.scratch.data_ptr() + 256, self.n, self.scratch.data_ptr(), self._stream()))
+
+    def parse_pack_only(self):
+        check(lib().lzs_b200_parse_pack_batch_device(
+            self.raw.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(), self.scratch.data_ptr() + 256,
+            self.comp.data_ptr(), self.comp_off.data_ptr(), self.comp_cap.data_ptr(), self.comp_len.data_ptr(),
+            self.n, self._stream()))
+
+    def decompress(self):
+        check(lib().lzs_b200_decompress_batch_device(
+            self.comp.data_ptr(), self.comp_off.data_ptr(), self.comp_len.data_ptr(),
+            self.dec.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(), self.dec_len.data_ptr(),
+            self.n, self.scratch.data_ptr(), self.scratch.numel(), self._stream()))
+
+    def roundtrip_ok(self):
+        t = self.torch
+        return bool(t.equal(self.dec[:self.total], self.raw[:self.total])) and \
+            bool(t.equal(self.dec_len, self.raw_len))
+
+    def compressed_bytes(self):
+        return int(self.comp_len.to(self.torch.int64).sum().item())

@@ -1,0 +1,195 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI (liblzs.so),
+against the oracle / committed reference outputs.  Bit-exact, no tolerance: everything
+on this path is integer and byte work."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from gpu_common import binding
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    b = binding()
+    b.lib()
+    assert b.lib().lzs_b200_device_count() > 0, "no CUDA device visible to liblzs.so"
+    return b
+
+
+def _golden(name):
+    return open(os.path.join(helpers.GOLDEN_DIR, name), "rb").read()
+
+
+def length_bits(rep):
+    if rep <= 1:
+        return 9 * rep
+    if rep <= 4:
+        return 2
+    if rep <= 7:
+        return 4
+    return ((rep + 22) // 15) * 4
+
+
+def test_reference_golden_vector_single_call(B):
+    """c/src/test/test-lzs-decompression.c:34-96 through lzs_decompress AND lzs_compress."""
+    comp, plain = _golden("golden1_compressed.bin"), _golden("golden1_plain.bin")
+    assert B.lzs_decompress(comp, len(plain) + 520) == plain
+    assert B.lzs_compress(plain) == comp
+    assert B.lzs_simple_compress(plain) == comp
+    assert B.lzs_compress(b"") == bytes([0xC0, 0x00])
+    assert B.lzs_compress(b"a") == bytes([0x30, 0xE0, 0x00])
+
+
+def test_reference_size_law_uncompressible(B):
+    """c/src/test/test-lzs.c:93-119 for every prefix length, as one batch."""
+    seq = _golden("uncompressible.bin")
+    data = [seq[:n] for n in range(len(seq) + 1)]
+    comp = B.compress_streams(data, caps=[1000] * len(data))
+    for n, c in enumerate(comp):
+        assert len(c) == (n * 9 + 9 + 7) // 8
+    assert B.decompress_streams(comp, [1000] * len(data)) == data
+
+
+def test_reference_size_law_repeated_byte(B):
+    """c/src/test/test-lzs.c:121-167 for n = 0..1000, as one batch."""
+    data = [b"X" * n for n in range(1001)]
+    comp = B.compress_streams(data, caps=[1000] * len(data))
+    for n, c in enumerate(comp):
+        bits = 0 if n == 0 else 9 if n == 1 else 18 if n == 2 else 9 + 2 + 7 + length_bits(n - 1)
+        assert len(c) == (bits + 9 + 7) // 8, n
+    assert B.decompress_streams(comp, [1000] * len(data)) == data
+
+
+def test_committed_reference_outputs(B):
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "ref_cases.npz"))
+    names = [k[4:] for k in z.files if k.startswith("in__")]
+    data = [z["in__" + k].tobytes() for k in names]
+    want = [z["out__" + k].tobytes() for k in names]
+    assert B.compress_streams(data) == want
+    assert B.decompress_streams(want, [len(d) + 9 for d in data]) == data
+    keys = [k for k in z.files if k.startswith("dec_in__")]
+    got = B.decompress_streams([z[k].tobytes() for k in keys], [int(k.split("__")[2]) for k in keys])
+    for k, g in zip(keys, got):
+        assert g == z["dec_out__" + k[len("dec_in__"):]].tobytes(), k
+
+
+def test_edge_cases_and_truncated_output(B):
+    o = helpers.oracle()
+    cases = helpers.edge_case_inputs()
+    data = list(cases.values())
+    full = [o.compress(d) for d in data]
+    assert B.compress_streams(data) == full
+    caps = [max(0, len(f) - 1 - (i % 7)) for i, f in enumerate(full)]
+    assert B.compress_streams(data, caps=caps) == [f[:c] for f, c in zip(full, caps)]
+    half = [len(d) // 2 for d in data]
+    assert B.decompress_streams(full, half) == [d[:h] for d, h in zip(data, half)]
+
+
+def test_random_bitstrings_decode_like_the_reference(B):
+    rng = np.random.default_rng(99)
+    o = helpers.oracle()
+    streams = [rng.integers(0, 256, int(rng.integers(0, 500)), dtype=np.uint8).tobytes() for _ in range(400)]
+    caps = [int(rng.integers(0, 6000)) for _ in streams]
+    got = B.decompress_streams(streams, caps)
+    for s, c, g in zip(streams, caps, got):
+        assert g == o.decompress(s, c)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_decoder_lane_widths(B, lanes):
+    o = helpers.oracle()
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 20000, first_index=i).tobytes() for i in range(9)]
+    comp = [o.compress(d) for d in data]
+    B.check(B.lib().lzs_b200_set_decode_lanes(lanes))
+    try:
+        assert B.decompress_streams(comp, [len(d) for d in data]) == data
+    finally:
+        B.lib().lzs_b200_set_decode_lanes(8)
+
+
+def _cpu_compress_all(chunks):
+    """Reference build when present (fast), else the oracle restatement."""
+    c = helpers.reference() or helpers.oracle()
+    return [c.compress(x) for x in chunks]
+
+
+@pytest.mark.parametrize("kind,chunk,count", [
+    (helpers.CORPUS_TEXT, 65536, 6), (helpers.CORPUS_BINARY, 65536, 6), (helpers.CORPUS_RANDOM, 65536, 3),
+    (helpers.CORPUS_MIXED, 4096, 48), (helpers.CORPUS_MIXED, 262144, 3), (helpers.CORPUS_PACKET, 1500, 600),
+    (helpers.CORPUS_MIXED, 1048576, 1),
+])
+def test_corpus_streams_bit_exact(B, kind, chunk, count):
+    buf = helpers.corpus(kind, count, chunk, seed=0x5EED0000 + chunk)
+    chunks = [buf[i * chunk:(i + 1) * chunk].tobytes() for i in range(count)]
+    want = _cpu_compress_all(chunks)
+    got = B.compress_streams(chunks)
+    assert got == want
+    assert B.decompress_streams(got, [chunk] * count) == chunks
+
+
+def test_match_table_equals_bruteforce_rule(B):
+    """K1 alone: per-position (length, offset) against the oracle's statement of the rule."""
+    import torch
+    chunk, count = 20000, 6
+    buf = helpers.corpus(helpers.CORPUS_MIXED, count, chunk, seed=0x5EED0000 + 77)
+    db = B.DeviceBatch(chunk * count, chunk)
+    db.raw[:chunk * count].copy_(torch.from_numpy(buf))
+    db.match_only()
+    torch.cuda.synchronize()
+    m = db.scratch[256:256 + 2 * chunk * count].cpu().numpy().view(np.uint16)
+    for i in range(count):
+        ln, off = helpers.oracle_all_matches(buf[i * chunk:(i + 1) * chunk].tobytes())
+        want = (ln.astype(np.uint16) << 11) | off
+        assert (m[i * chunk:(i + 1) * chunk] == want).all(), i
+
+
+def test_device_corpus_matches_host_corpus(B):
+    import torch
+    for kind in (B.CORPUS_TEXT, B.CORPUS_BINARY, B.CORPUS_RANDOM, B.CORPUS_MIXED, B.CORPUS_PACKET):
+        db = B.DeviceBatch(6 * 3000, 3000)
+        db.fill(kind, 0x5EED0000 + 5, first_index=7)
+        torch.cuda.synchronize()
+        host = helpers.corpus(kind, 6, 3000, seed=0x5EED0000 + 5, first_index=7)
+        assert (db.raw[:18000].cpu().numpy() == host).all()
+
+
+def test_full_size_roundtrip_1gib_64k_chunks(B):
+    """BASELINE config 2 at full size: size-independent properties (round trip, sizes within
+    LZS_COMPRESSED_MAX) plus byte-exact comparison of sampled chunks with the CPU codec."""
+    import torch
+    total, chunk = 1 << 30, 65536
+    db = B.DeviceBatch(total, chunk)
+    db.fill(B.CORPUS_MIXED, 0x5EED0000 + 2)
+    db.compress()
+    db.decompress()
+    torch.cuda.synchronize()
+    assert db.roundtrip_ok()
+    lens = db.comp_len.cpu().numpy()
+    assert lens.max() <= B.compressed_max(chunk) and lens.min() > 2
+    ref = helpers.reference() or helpers.oracle()
+    for s in (0, 1, 2, 5000, 9001, 16383):
+        raw = db.raw[s * chunk:(s + 1) * chunk].cpu().numpy().tobytes()
+        got = db.comp[s * db.comp_stride:s * db.comp_stride + int(lens[s])].cpu().numpy().tobytes()
+        assert got == ref.compress(raw), s
+
+
+def test_full_size_packets_roundtrip(B):
+    """BASELINE config 3 shape: 1 Mi packets of 1500 bytes, each its own stream."""
+    import torch
+    n, plen = 1 << 20, 1500
+    db = B.DeviceBatch(n * plen, plen)
+    db.fill(B.CORPUS_PACKET, 0x5EED0000 + 3)
+    db.compress()
+    db.decompress()
+    torch.cuda.synchronize()
+    assert db.roundtrip_ok()
+    lens = db.comp_len.cpu().numpy()
+    ref = helpers.reference() or helpers.oracle()
+    for s in (0, 1, 2, 77777, n - 1):
+        raw = db.raw[s * plen:(s + 1) * plen].cpu().numpy().tobytes()
+        got = db.comp[s * db.comp_stride:s * db.comp_stride + int(lens[s])].cpu().numpy().tobytes()
+        assert got == ref.compress(raw), s
