@@ -20,25 +20,34 @@
  *
  *   P_k is "previous equal element" over the sequence of k-grams.  One warp per
  *   level k keeps a 4096-slot last-occurrence table in shared memory and inserts
- *   positions in order, 32 at a time: __match_any_sync finds predecessors inside
- *   the batch, the table gives the predecessor from earlier batches.  Each
- *   position stores the distance to its predecessor in the same SLOT; slots are
- *   hashes, so a query verifies bytes and, on a foreign entry, follows the
+ *   positions in order, 32 at a time.  Every lane reads the old head of its slot,
+ *   all lanes store their position, and a read-back tells a lane whether another
+ *   lane of the same batch shares its slot; only then are the few duplicated
+ *   lanes ordered with MATCH.ANY (whose cost on sm_100a grows with the number of
+ *   distinct keys: ~12 cycles each, so it is never run on 32 distinct slots).
+ *   Each position stores the distance to its predecessor in the same SLOT; slots
+ *   are hashes, so a query verifies bytes and, on a foreign entry, follows the
  *   distance chain (every in-window position of the slot is on it, nearest
- *   first).  Table and chain garbage (stale entries, aliasing) can only produce
- *   candidates that fail the byte check, never a wrong answer -- the same
+ *   first).  Table and chain garbage (stale entries, 16-bit aliasing) can only
+ *   produce candidates that fail the byte check, never a wrong answer -- the same
  *   argument that lets the reference run on uninitialised tables
  *   (lzs-compression.c:253-254).
  *
- *   A query probes level 2 first (incompressible data stops there), then
- *   bisects the remaining levels; a verified candidate of length l found at
- *   level k is also the nearest candidate at level l, so the search jumps.
+ *   A query probes level 2 first (incompressible data stops there) and then moves
+ *   upwards; a verified candidate of length l found at level k is also the nearest
+ *   candidate at level l, so the next level tried is l + 1, and the first level
+ *   without a candidate ends the search.
  *
- * Layout: one persistent CTA per SM (192 KiB of shared memory: 11 head tables,
- * 11 link rings, a ring of 4-byte grams), streams pulled from a global counter,
- * each stream walked in 1024-position tiles.  Output: one uint16 per input byte,
- * (len << 11) | offset, consumed by the parse kernel.
+ * Layout: one persistent CTA per SM (208 KiB of shared memory: 11 head tables,
+ * 11 link rings, a ring of 4-byte grams), streams pulled from a global counter and
+ * walked in 992-position tiles.  The CTA is warp specialised: 11 build warps (one
+ * per level) run one tile ahead of 13 query warps; the two groups hand tiles over
+ * through named barriers (double buffered).  Positions are numbered continuously
+ * across the streams a CTA processes ("virtual positions"), so the rings need no
+ * clearing between streams; a candidate is valid only if its distance does not
+ * exceed the position inside the current stream.
  *
+ * Output: one uint16 per input byte, (len << 11) | offset, consumed by K2.
  * HBM traffic per input byte: 1 B read + 2 B written (intermediate).
  */
 #ifndef LZS_B200_K1_MATCH_CUH
@@ -50,11 +59,25 @@ namespace lzs {
 
 constexpr int      kK1Levels = 11;          /* k = 2 .. 12 */
 constexpr uint32_t kK1Slots = 4096;
-constexpr uint32_t kK1Ring = 4096;          /* >= 2047 + tile + 8 */
-constexpr uint32_t kK1Tile = 1024;
-constexpr int      kK1Threads = 512;
-constexpr size_t   kK1SmemBytes =
-    static_cast<size_t>(kK1Levels) * kK1Slots * 2 + static_cast<size_t>(kK1Levels) * kK1Ring * 2 + kK1Ring * 4;
+constexpr uint32_t kK1LinkRing = 4096;      /* >= 2047 + 2 * (tile + gap)          */
+constexpr uint32_t kK1WRing = 8192;
+constexpr uint32_t kK1Tile = 992;           /* 31 batches of 32                    */
+constexpr uint32_t kK1StreamGap = 16;       /* virtual positions between streams   */
+constexpr int      kK1BuildWarps = kK1Levels;
+constexpr int      kK1QueryWarps = 13;
+constexpr int      kK1Threads = 32 * (kK1BuildWarps + kK1QueryWarps);
+constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
+constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
+constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 +
+                                static_cast<size_t>(kK1Levels) * kK1LinkRing * 2 + kK1WRing * 4;
+static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
+
+enum { kBarBuild = 1, kBarFull0 = 2, kBarFull1 = 3, kBarEmpty0 = 4, kBarEmpty1 = 5 };
+constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
+
+struct K1Tile {
+    uint32_t sid, t0, tile_n, n, v0;
+};
 
 /* mask selecting the low `bytes` bytes of a little-endian word, bytes in 1..4 */
 __device__ __forceinline__ constexpr uint32_t low_bytes_mask(int bytes)
@@ -62,25 +85,37 @@ __device__ __forceinline__ constexpr uint32_t low_bytes_mask(int bytes)
     return bytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * bytes)) - 1u);
 }
 
-/* table slot of the K-gram whose bytes are the first K bytes of (w0, w1, w2) */
-template <int K>
-__device__ __forceinline__ uint32_t gram_slot(uint32_t w0, uint32_t w1, uint32_t w2)
+/* Hash of the k-gram that starts the 12 bytes (w0, w1, w2): bits 31..20 are the table
+ * slot, bits 19..15 a 5-bit tag kept beside every chain link so that a query can
+ * reject most foreign entries of its slot without touching their bytes. */
+__device__ __forceinline__ uint32_t gram_hash(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t m0,
+                                              uint32_t m1, uint32_t m2)
 {
-    uint32_t h;
-    if (K <= 4) {
-        h = (w0 & low_bytes_mask(K)) * 0x9E3779B1u;
-    } else if (K <= 8) {
-        h = w0 * 0x9E3779B1u;
-        h = (h ^ (w1 & low_bytes_mask(K - 4))) * 0x85EBCA77u;
-    } else {
-        h = w0 * 0x9E3779B1u;
-        h = (h ^ w1) * 0x85EBCA77u;
-        h = (h ^ (w2 & low_bytes_mask(K - 8))) * 0xC2B2AE3Du;
-    }
+    uint32_t h = (w0 & m0) * 0x9E3779B1u;
+    h = (h ^ (w1 & m1)) * 0x85EBCA77u;
+    h = (h ^ (w2 & m2)) * 0xC2B2AE3Du;
     h ^= h >> 15;
     h *= 0x27D4EB2Fu;
-    return h >> 20;                          /* 12 bits */
+    return h;
 }
+__device__ __forceinline__ uint32_t gram_hash_k(uint32_t k, uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const uint32_t m0 = k >= 4u ? 0xFFFFFFFFu : ((1u << (8u * k)) - 1u);
+    const uint32_t m1 = k >= 8u ? 0xFFFFFFFFu : (k <= 4u ? 0u : ((1u << (8u * (k - 4u))) - 1u));
+    const uint32_t m2 = k >= 12u ? 0xFFFFFFFFu : (k <= 8u ? 0u : ((1u << (8u * (k - 8u))) - 1u));
+    return gram_hash(w0, w1, w2, m0, m1, m2);
+}
+template <int K>
+__device__ __forceinline__ uint32_t gram_hash_c(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    constexpr uint32_t m0 = low_bytes_mask(K >= 4 ? 4 : K);
+    constexpr uint32_t m1 = K <= 4 ? 0u : low_bytes_mask(K >= 8 ? 4 : K - 4);
+    constexpr uint32_t m2 = K <= 8 ? 0u : low_bytes_mask(K >= 12 ? 4 : K - 8);
+    return gram_hash(w0, w1, w2, m0, m1, m2);
+}
+constexpr uint32_t kSlotShift = 20;          /* slot = h >> 20 (12 bits)                    */
+constexpr uint32_t kTagShift = 15;           /* tag  = (h >> 15) & 31                       */
+constexpr uint32_t kLinkDistMask = 0x7FFu;   /* link entry: (tag << 11) | distance          */
 
 /* common prefix length (0..12) of two 12-byte strings given as LE words */
 __device__ __forceinline__ uint32_t lcp12(uint32_t a0, uint32_t a1, uint32_t a2,
@@ -93,81 +128,103 @@ __device__ __forceinline__ uint32_t lcp12(uint32_t a0, uint32_t a1, uint32_t a2,
     return 12u;
 }
 
+template <int K>
+__device__ __forceinline__ uint32_t k1_hash_at(const uint32_t *W, uint32_t v)
+{
+    return gram_hash_c<K>(W[v & (kK1WRing - 1)], W[(v + 4) & (kK1WRing - 1)], W[(v + 8) & (kK1WRing - 1)]);
+}
+
 /* Insert the positions of one tile into level K's table, in order, and record
  * for each the distance to the previous position of the same slot (0 = none in
  * the window).  Executed by one whole warp. */
 template <int K>
 __device__ __forceinline__ void k1_build_level(uint16_t *heads, uint16_t *links, const uint32_t *W,
-                                               uint32_t t0, uint32_t tile_n, uint32_t epoch)
+                                               uint32_t v0, uint32_t t0, uint32_t tile_n)
 {
     const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
     uint16_t      *hd = heads + (K - 2) * kK1Slots;
-    uint16_t      *lk = links + (K - 2) * kK1Ring;
+    uint16_t      *lk = links + (K - 2) * kK1LinkRing;
+    uint32_t       hnext = k1_hash_at<K>(W, v0 + t0 + lane);
     for (uint32_t b = 0; b < tile_n; b += 32) {
         const uint32_t i = t0 + b + lane;
+        const uint32_t v = v0 + i;
         const bool     act = (b + lane) < tile_n;
-        const uint32_t w0 = W[i & (kK1Ring - 1)];
-        const uint32_t w1 = W[(i + 4) & (kK1Ring - 1)];
-        const uint32_t w2 = W[(i + 8) & (kK1Ring - 1)];
-        const uint32_t slot = act ? gram_slot<K>(w0, w1, w2) : (0x10000u | lane);
-        const uint32_t grp = __match_any_sync(LZS_FULL_MASK, slot);
-        const uint32_t lower = grp & ((1u << lane) - 1u);
-        const uint32_t pos16 = (epoch + i) & 0xFFFFu;
-        if (act) {
-            uint32_t dist;
-            if (lower) dist = lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(lower))));
-            else       dist = (pos16 - hd[slot]) & 0xFFFFu;
-            if (dist > umin32(kWindow, i)) dist = 0;
-            lk[i & (kK1Ring - 1)] = static_cast<uint16_t>(dist);
-        }
-        __syncwarp();                        /* all table reads before any insert */
-        if (act && (grp >> lane) == 1u) hd[slot] = static_cast<uint16_t>(pos16);
+        const uint32_t pos16 = v & 0xFFFFu;
+        const uint32_t cur = hnext >> kSlotShift;
+        const uint32_t tag = (hnext >> kTagShift) & 31u;
+        hnext = k1_hash_at<K>(W, v + 32);    /* next batch: independent of the table, overlaps below */
+
+        const uint32_t old = act ? hd[cur] : 0u;
+        __syncwarp();                        /* every lane has the pre-batch head       */
+        if (act) hd[cur] = static_cast<uint16_t>(pos16);
         __syncwarp();
-    }
-}
-
-/* Walk level k's chain from position i: first in-window candidate whose common
- * prefix (capped at M) reaches k.  Returns that prefix length, or 0. */
-__device__ __forceinline__ uint32_t k1_probe(const uint16_t *links, const uint32_t *W, uint32_t k,
-                                             uint32_t i, uint32_t maxd, uint32_t M, uint32_t w0,
-                                             uint32_t w1, uint32_t w2, uint32_t &dist_out)
-{
-    const uint16_t *lk = links + (k - 2) * kK1Ring;
-    uint32_t        tot = 0;
-    uint32_t        d = lk[i & (kK1Ring - 1)];
-    while (d != 0) {
-        tot += d;
-        if (tot > maxd) break;
-        const uint32_t j = i - tot;
-        const uint32_t l = umin32(lcp12(w0, w1, w2, W[j & (kK1Ring - 1)], W[(j + 4) & (kK1Ring - 1)],
-                                        W[(j + 8) & (kK1Ring - 1)]), M);
-        if (l >= k) {
-            dist_out = tot;
-            return l;
+        const uint32_t back = act ? hd[cur] : pos16;
+        const bool     loser = back != pos16; /* another lane of this batch owns my slot */
+        uint32_t       dist = (pos16 - old) & 0xFFFFu;
+        if (__ballot_sync(LZS_FULL_MASK, loser) != 0u) {
+            /* order the duplicated lanes only: the slot's winner and its losers */
+            const uint32_t base16 = (v0 + t0 + b) & 0xFFFFu;
+            const uint32_t named =
+                __reduce_or_sync(LZS_FULL_MASK, loser ? (1u << ((back - base16) & 31u)) : 0u);
+            const bool     dup = act && (loser || ((named >> lane) & 1u));
+            const uint32_t grp = __match_any_sync(LZS_FULL_MASK, dup ? cur : 0xFFFFFFFFu);
+            if (dup) {
+                const uint32_t lower = grp & lt;
+                if (lower) dist = lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(lower))));
+                if ((grp >> lane) == 1u && loser) hd[cur] = static_cast<uint16_t>(pos16);  /* last one owns the head */
+            }
+            __syncwarp();
         }
-        d = lk[j & (kK1Ring - 1)];
+        if (act) {
+            if (dist > umin32(kWindow, i)) dist = 0;
+            lk[v & (kK1LinkRing - 1)] = static_cast<uint16_t>(dist | (tag << 11));
+        }
     }
-    return 0;
 }
 
-__device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint32_t *W, uint32_t i, uint32_t n)
+/* One query = a single flat loop of chain steps (no nested loops, so lanes of a warp
+ * stay together).  Levels are tried upwards: a verified candidate of length l at level
+ * k answers every level up to l, so the next level tried is l + 1, and the first level
+ * whose chain ends without a verified candidate ends the search ("some candidate
+ * reaches k" is monotone in k).  Every chain link carries the 5-bit tag of the entry
+ * it belongs to, so a foreign entry costs one shared-memory load. */
+__device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint32_t *W, uint32_t v0,
+                                             uint32_t i, uint32_t n)
 {
     const uint32_t M = umin32(kSearchMax, n - i);
     const uint32_t maxd = umin32(kWindow, i);
     if (M < kMinLen || maxd == 0) return 0;
-    const uint32_t w0 = W[i & (kK1Ring - 1)];
-    const uint32_t w1 = W[(i + 4) & (kK1Ring - 1)];
-    const uint32_t w2 = W[(i + 8) & (kK1Ring - 1)];
-    uint32_t bd = 0;
-    uint32_t best = k1_probe(links, W, 2, i, maxd, M, w0, w1, w2, bd);
-    if (best == 0) return 0;
-    uint32_t lo = best + 1, hi = M;
-    while (lo <= hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        uint32_t       dd = 0;
-        const uint32_t l = k1_probe(links, W, mid, i, maxd, M, w0, w1, w2, dd);
-        if (l) { best = l; bd = dd; lo = l + 1; }
-        else   { hi = mid - 1; }
+    const uint32_t v = v0 + i;
+    const uint32_t w0 = W[v & (kK1WRing - 1)];
+    const uint32_t w1 = W[(v + 4) & (kK1WRing - 1)];
+    const uint32_t w2 = W[(v + 8) & (kK1WRing - 1)];
+    uint32_t best = 0, bd = 0;
+    uint32_t k = kMinLen;
+    const uint16_t *lk = links;                              /* level k's ring              */
+    uint32_t e = lk[v & (kK1LinkRing - 1)];                  /* own entry: tag + first link */
+    uint32_t tag = e >> 11;
+    uint32_t d = e & kLinkDistMask;
+    uint32_t tot = 0;
+    for (;;) {
+        tot += d;
+        if (d == 0 || tot > maxd) break;                     /* level k has no candidate: done */
+        const uint32_t j = v - tot;
+        e = lk[j & (kK1LinkRing - 1)];
+        d = e & kLinkDistMask;
+        if ((e >> 11) != tag) continue;                      /* foreign entry of this slot  */
+        const uint32_t l = umin32(lcp12(w0, w1, w2, W[j & (kK1WRing - 1)], W[(j + 4) & (kK1WRing - 1)],
+                                        W[(j + 8) & (kK1WRing - 1)]), M);
+        if (l < k) continue;
+        best = l;                                            /* nearest candidate of length l */
+        bd = tot;
+        if (l >= M) break;
+        k = l + 1;                                           /* next level to try           */
+        lk = links + (k - 2) * kK1LinkRing;
+        e = lk[v & (kK1LinkRing - 1)];
+        tag = e >> 11;
+        d = e & kLinkDistMask;
+        tot = 0;
     }
     return (best << kMatchOffBits) | bd;
 }
@@ -180,59 +237,84 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     LZS_DYN_SMEM(uint8_t, smem);
     uint16_t *heads = reinterpret_cast<uint16_t *>(smem);
     uint16_t *links = heads + kK1Levels * kK1Slots;
-    uint32_t *W = reinterpret_cast<uint32_t *>(links + kK1Levels * kK1Ring);
+    uint32_t *W = reinterpret_cast<uint32_t *>(links + kK1Levels * kK1LinkRing);
     __shared__ uint32_t s_sid;
+    __shared__ K1Tile   s_tile[2];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
 
-    for (uint32_t x = tid; x < kK1Levels * (kK1Slots + kK1Ring); x += kK1Threads) heads[x] = 0;
-    uint32_t epoch = 1;                      /* running 16-bit position base across streams */
+    for (uint32_t x = tid; x < kK1Levels * (kK1Slots + kK1LinkRing); x += kK1Threads) heads[x] = 0;
+    __syncthreads();
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_sid = atomicAdd(next_stream, 1u);
-        __syncthreads();
-        const uint32_t sid = s_sid;
-        if (sid >= n_streams) break;
+    if (warp < static_cast<uint32_t>(kK1BuildWarps)) {
+        /* ================= producer: fill grams, build the 11 levels ================= */
+        uint32_t g = 0;                      /* tiles produced so far                   */
+        uint32_t vnext = 4096;               /* virtual position of the next stream     */
+        for (;;) {
+            if (tid == 0) s_sid = atomicAdd(next_stream, 1u);
+            named_sync(kBarBuild, kK1BuildThreads);
+            const uint32_t sid = s_sid;
+            named_sync(kBarBuild, kK1BuildThreads);
+            if (sid >= n_streams) break;
 
-        const uint32_t n = in_len[sid];
-        const uint8_t *src = in + in_off[sid];
-        const uint8_t *end = src + n;
-        match_t       *mout = matches + in_off[sid];
+            const uint32_t n = in_len[sid];
+            const uint8_t *src = in + in_off[sid];
+            const uint8_t *end = src + n;
+            const uint32_t v0 = vnext;
+            vnext = v0 + n + kK1StreamGap;
 
-        for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile) {
-            const uint32_t tile_n = umin32(kK1Tile, n - t0);
-            /* 4-byte grams for the new positions (+8 look-ahead for 12-byte compares) */
-            const uint32_t p_lo = (t0 == 0) ? 0u : t0 + 8u;
-            const uint32_t p_hi = t0 + kK1Tile + 8u;
-            for (uint32_t p = p_lo + tid; p < p_hi; p += kK1Threads)
-                W[p & (kK1Ring - 1)] = (p < n) ? load4_unaligned(src + p, end) : 0u;
-            __syncthreads();
+            for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
+                const uint32_t buf = g & 1u;
+                if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
+                const uint32_t tile_n = umin32(kK1Tile, n - t0);
+                /* 4-byte grams of the new positions (+8 look-ahead for 12-byte compares) */
+                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + 8u;
+                const uint32_t p_hi = umin32(t0 + kK1Tile + 8u, n + 12u);
+                for (uint32_t p = p_lo + tid; p < p_hi; p += kK1BuildThreads)
+                    W[(v0 + p) & (kK1WRing - 1)] = (p < n) ? load4_unaligned(src + p, end) : 0u;
+                named_sync(kBarBuild, kK1BuildThreads);
 
-            switch (warp) {
-                case 0:  k1_build_level<2>(heads, links, W, t0, tile_n, epoch); break;
-                case 1:  k1_build_level<3>(heads, links, W, t0, tile_n, epoch); break;
-                case 2:  k1_build_level<4>(heads, links, W, t0, tile_n, epoch); break;
-                case 3:  k1_build_level<5>(heads, links, W, t0, tile_n, epoch); break;
-                case 4:  k1_build_level<6>(heads, links, W, t0, tile_n, epoch); break;
-                case 5:  k1_build_level<7>(heads, links, W, t0, tile_n, epoch); break;
-                case 6:  k1_build_level<8>(heads, links, W, t0, tile_n, epoch); break;
-                case 7:  k1_build_level<9>(heads, links, W, t0, tile_n, epoch); break;
-                case 8:  k1_build_level<10>(heads, links, W, t0, tile_n, epoch); break;
-                case 9:  k1_build_level<11>(heads, links, W, t0, tile_n, epoch); break;
-                case 10: k1_build_level<12>(heads, links, W, t0, tile_n, epoch); break;
-                default: break;
+                switch (warp) {
+                    case 0:  k1_build_level<2>(heads, links, W, v0, t0, tile_n); break;
+                    case 1:  k1_build_level<3>(heads, links, W, v0, t0, tile_n); break;
+                    case 2:  k1_build_level<4>(heads, links, W, v0, t0, tile_n); break;
+                    case 3:  k1_build_level<5>(heads, links, W, v0, t0, tile_n); break;
+                    case 4:  k1_build_level<6>(heads, links, W, v0, t0, tile_n); break;
+                    case 5:  k1_build_level<7>(heads, links, W, v0, t0, tile_n); break;
+                    case 6:  k1_build_level<8>(heads, links, W, v0, t0, tile_n); break;
+                    case 7:  k1_build_level<9>(heads, links, W, v0, t0, tile_n); break;
+                    case 8:  k1_build_level<10>(heads, links, W, v0, t0, tile_n); break;
+                    case 9:  k1_build_level<11>(heads, links, W, v0, t0, tile_n); break;
+                    default: k1_build_level<12>(heads, links, W, v0, t0, tile_n); break;
+                }
+                if (tid == 0) {
+                    K1Tile d;
+                    d.sid = sid; d.t0 = t0; d.tile_n = tile_n; d.n = n; d.v0 = v0;
+                    s_tile[buf] = d;
+                }
+                named_arrive(kBarFull0 + static_cast<int>(buf), kK1Threads);
             }
-            __syncthreads();
-
-            for (uint32_t r = tid; r < tile_n; r += kK1Threads) {
-                const uint32_t i = t0 + r;
-                mout[i] = static_cast<match_t>(k1_query(links, W, i, n));
-            }
-            __syncthreads();
         }
-        epoch = (epoch + n) & 0xFFFFu;
+        const uint32_t buf = g & 1u;
+        if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
+        if (tid == 0) s_tile[buf].sid = kK1EndOfWork;
+        named_arrive(kBarFull0 + static_cast<int>(buf), kK1Threads);
+    } else {
+        /* ================= consumer: one query per position ================= */
+        const uint32_t qtid = tid - kK1BuildThreads;
+        for (uint32_t g = 0;; g++) {
+            const uint32_t buf = g & 1u;
+            named_sync(kBarFull0 + static_cast<int>(buf), kK1Threads);
+            const K1Tile d = s_tile[buf];
+            if (d.sid == kK1EndOfWork) break;
+            match_t *mout = matches + in_off[d.sid];
+            for (uint32_t r = qtid; r < d.tile_n; r += kK1QueryThreads) {
+                const uint32_t i = d.t0 + r;
+                mout[i] = static_cast<match_t>(k1_query(links, W, d.v0, i, d.n));
+            }
+            named_arrive(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
+        }
     }
 }
 

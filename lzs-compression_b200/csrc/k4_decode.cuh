@@ -11,13 +11,15 @@
  *
  * Mapping: G lanes of a warp decode one stream (G = 4/8/16/32), so one warp
  * instruction serves 32/G streams.  The token parse is inherently serial per
- * stream, so the lanes of a group run it redundantly (no divergence inside the
- * group) and split the back-reference copy.  History lives in a 2 KiB shared-
- * memory ring per stream (the window is 2047 bytes); output leaves the ring in
- * 16*G-byte blocks with 16-byte vector stores.  Groups are persistent and pull
- * stream indices from a global counter, which balances streams whose token
- * counts differ (incompressible vs. text).
+ * stream, so the lanes of a group run it redundantly and split the back-reference
+ * copy.  All 32/G groups of a warp advance in lock step, one token per iteration,
+ * under warp-uniform control flow: every collective uses the full mask (a
+ * variable member mask makes nvcc emit MATCH.ANY, ~50-390 cycles on sm_100a), and
+ * a group whose stream ended simply idles until it has fetched the next stream
+ * index from a global counter (which also balances incompressible vs. text chunks).
  *
+ * History lives in a 2 KiB shared-memory ring per stream (the window is 2047
+ * bytes); output leaves the ring in 16*G-byte blocks with 16-byte vector stores.
  * Overlapping copies (offset < length) need no serialisation: byte k of a match
  * equals history byte (k mod offset), which was written by an earlier token.
  *
@@ -37,6 +39,20 @@ constexpr uint32_t kDecRing = 2048;
 template <int G>
 constexpr size_t k4_smem_bytes() { return static_cast<size_t>(kDecThreads / G) * kDecRing; }
 
+/* One compressed stream seen as aligned big-endian 32-bit words. */
+struct DecInput {
+    const uint32_t *wbase;
+    uint32_t        nwords;
+    uint32_t        tail;     /* valid bytes in the last word, 0 = all four */
+    __device__ __forceinline__ uint32_t fetch(uint32_t w) const
+    {
+        if (w >= nwords) return 0u;
+        uint32_t v = bswap32(__ldg(wbase + w));
+        if (w == nwords - 1u && tail) v &= 0xFFFFFFFFu << (8u * (4u - tail));
+        return v;                                       /* bits past the end read as zero */
+    }
+};
+
 template <int G>
 __global__ void __launch_bounds__(kDecThreads)
 k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
@@ -47,143 +63,156 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     LZS_DYN_SMEM(uint8_t, smem);
     const uint32_t lane = lane_id();
     const uint32_t gl = lane % G;
-    const uint32_t gmask = (G == 32) ? LZS_FULL_MASK : (((1u << (G & 31)) - 1u) << (lane - gl));
     uint8_t *ring = smem + static_cast<size_t>(threadIdx.x / G) * kDecRing;
+    constexpr int kPass = (static_cast<int>(kMaxExtLen) + G - 1) / G;
+
+    /* per-stream state; identical in all lanes of a group */
+    bool     active = false, exhausted = false, ext = false, vec_ok = false;
+    uint32_t sid = 0, cap = 0, pos = 0, flushed = 0, off = 1, wi = 0, nextw = 0;
+    int      nb = 0;
+    uint64_t win = 0, avail = 0;
+    uint8_t *dst = nullptr;
+    DecInput src{nullptr, 0, 0};
 
     for (;;) {
-        uint32_t sid = 0;
-        if (gl == 0) sid = atomicAdd(next_stream, 1u);
-        sid = __shfl_sync(gmask, sid, 0, G);
-        if (sid >= n_streams) break;
-
-        const uint8_t *src = in + in_off[sid];
-        const uint32_t nin = in_len[sid];
-        uint8_t       *dst = out + out_off[sid];
-        const uint32_t cap = out_cap[sid];
-        const bool     vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
-
-        /* aligned 32-bit view of the stream; `skip` leading bits belong to the
-         * bytes before src inside the first aligned word */
-        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-        const uint32_t *wbase = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
-        const uint32_t  lead = static_cast<uint32_t>(a & 3u);
-        const uint32_t  nbytes = lead + nin;
-        const uint32_t  nwords = (nbytes + 3u) >> 2;
-        const uint32_t  tail = nbytes & 3u;            /* valid bytes in the last word, 0 = all */
-
-        uint32_t wi = 0;
-        auto fetch = [&](uint32_t w) -> uint32_t {
-            if (w >= nwords) return 0u;
-            uint32_t v = bswap32(__ldg(wbase + w));
-            if (w == nwords - 1u && tail) v &= 0xFFFFFFFFu << (8u * (4u - tail));
-            return v;                                   /* bits past the end read as zero */
-        };
-        uint32_t nextw = fetch(wi++);
-        uint64_t win = 0;                               /* next bit is bit 63 */
-        int      nb = 0;                                /* bits held in win   */
-        uint64_t avail = static_cast<uint64_t>(nin) * 8u;   /* stream bits not yet consumed */
-
-        win = static_cast<uint64_t>(nextw) << 32;
-        nb = 32;
-        nextw = fetch(wi++);
-        win <<= 8u * lead;
-        nb -= static_cast<int>(8u * lead);
-
-        uint32_t pos = 0, flushed = 0, off = 0;
-        bool     ext = false;
-
-        for (;;) {
-            if (avail == 0 || pos >= cap) break;
-            if (nb <= 32) {
-                win |= static_cast<uint64_t>(nextw) << (32 - nb);
-                nb += 32;
-                nextw = fetch(wi++);
-            }
-            const uint32_t top = static_cast<uint32_t>(win >> 32);
-            uint32_t need, L, lit_byte = 0;
-            bool     lit = false;
-            if (!ext) {
-                if ((top >> 31) == 0u) {                /* literal: 0 + 8 bits */
-                    if (avail < 9u) break;
-                    need = 9u;
-                    lit_byte = (top >> 23) & 0xFFu;
-                    L = 1u;
-                    lit = true;
+        /* ---- idle groups fetch the next stream ---- */
+        const bool want = !active && !exhausted;
+        if (__any_sync(LZS_FULL_MASK, want)) {
+            uint32_t s = 0;
+            if (want && gl == 0) s = atomicAdd(next_stream, 1u);
+            s = __shfl_sync(LZS_FULL_MASK, s, 0, G);
+            if (want) {
+                if (s >= n_streams) {
+                    exhausted = true;
                 } else {
-                    const uint32_t is_short = (top >> 30) & 1u;
-                    const uint32_t hdr = is_short ? 9u : 13u;
-                    const uint32_t o = is_short ? ((top >> 23) & 0x7Fu) : ((top >> 19) & 0x7FFu);
-                    if (avail < hdr) break;
-                    if (o == 0u) {
-                        if (is_short) break;            /* end marker */
-                        win <<= 13;                     /* long offset 0: no length field */
-                        nb -= 13;
-                        avail -= 13u;
-                        continue;
-                    }
-                    const uint32_t code = (top << hdr) >> 28;
-                    uint32_t       w;
-                    if (code < 12u) { L = (code >> 2) + 2u; w = 2u; }
-                    else            { L = code - 7u;        w = 4u; }
-                    need = hdr + w;
-                    if (avail < need) break;
-                    off = o;
-                    ext = (L == kMaxShortLen);
+                    sid = s;
+                    const uint8_t  *p = in + in_off[sid];
+                    const uint32_t  nin = in_len[sid];
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+                    const uint32_t  lead = static_cast<uint32_t>(a & 3u);
+                    src.wbase = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+                    src.nwords = (lead + nin + 3u) >> 2;
+                    src.tail = (lead + nin) & 3u;
+                    dst = out + out_off[sid];
+                    cap = out_cap[sid];
+                    vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+                    avail = static_cast<uint64_t>(nin) * 8u;
+                    /* the `lead` bytes before the stream inside its first word are skipped */
+                    win = static_cast<uint64_t>(src.fetch(0)) << (32u + 8u * lead);
+                    nb = 32 - static_cast<int>(8u * lead);
+                    nextw = src.fetch(1);
+                    wi = 2;
+                    pos = 0;
+                    flushed = 0;
+                    off = 1;
+                    ext = false;
+                    active = true;
                 }
-            } else {                                    /* 4-bit continuation */
-                if (avail < 4u) break;
-                L = top >> 28;
-                need = 4u;
-                ext = (L == kMaxExtLen);
-            }
-            win <<= need;
-            nb -= static_cast<int>(need);
-            avail -= need;
-
-            L = umin32(L, cap - pos);
-            if (lit) {
-                if (gl == 0) ring[pos & (kDecRing - 1u)] = static_cast<uint8_t>(lit_byte);
-            } else {
-                /* The ring is one byte larger than the window, so the byte written for
-                 * k+1 lands on the slot that k reads at offset 2047: read everything
-                 * first, then write. */
-                constexpr int kPass = (static_cast<int>(kMaxExtLen) + G - 1) / G;
-                uint8_t       v[kPass];
-#pragma unroll
-                for (int t = 0; t < kPass; t++) {
-                    const uint32_t k = gl + static_cast<uint32_t>(t) * G;
-                    v[t] = 0;
-                    if (k < L) {
-                        uint32_t kk = k;
-                        if (kk >= off) kk %= off;       /* overlap: periodic extension */
-                        const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
-                        if (s >= 0) v[t] = ring[static_cast<uint32_t>(s) & (kDecRing - 1u)];
-                    }
-                }
-                __syncwarp(gmask);
-#pragma unroll
-                for (int t = 0; t < kPass; t++) {
-                    const uint32_t k = gl + static_cast<uint32_t>(t) * G;
-                    if (k < L) ring[(pos + k) & (kDecRing - 1u)] = v[t];
-                }
-            }
-            pos += L;
-            __syncwarp(gmask);
-
-            if (pos - flushed >= 16u * G) {
-                const uint32_t p = flushed + 16u * gl;
-                if (vec_ok) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(ring + (p & (kDecRing - 1u)));
-                    *reinterpret_cast<uint4 *>(dst + p) = v;
-                } else {
-                    for (uint32_t b = 0; b < 16u; b++) dst[p + b] = ring[(p + b) & (kDecRing - 1u)];
-                }
-                flushed += 16u * G;
             }
         }
-        for (uint32_t k = flushed + gl; k < pos; k += G) dst[k] = ring[k & (kDecRing - 1u)];
-        if (gl == 0) out_len[sid] = pos;
-        __syncwarp(gmask);
+        if (__all_sync(LZS_FULL_MASK, !active)) break;
+
+        /* ---- one token per active group ---- */
+        bool     done = false, lit = false;
+        uint32_t L = 0, lit_byte = 0;
+        if (active) {
+            if (avail == 0 || pos >= cap) {
+                done = true;
+            } else {
+                if (nb <= 32) {
+                    win |= static_cast<uint64_t>(nextw) << (32 - nb);
+                    nb += 32;
+                    nextw = src.fetch(wi++);
+                }
+                const uint32_t top = static_cast<uint32_t>(win >> 32);
+                uint32_t       need = 0;
+                if (!ext) {
+                    if ((top >> 31) == 0u) {            /* literal: 0 + 8 bits */
+                        need = 9u;
+                        lit_byte = (top >> 23) & 0xFFu;
+                        L = 1u;
+                        lit = true;
+                        if (avail < need) done = true;
+                    } else {
+                        const uint32_t is_short = (top >> 30) & 1u;
+                        const uint32_t hdr = is_short ? 9u : 13u;
+                        const uint32_t o = is_short ? ((top >> 23) & 0x7Fu) : ((top >> 19) & 0x7FFu);
+                        const uint32_t code = (top << hdr) >> 28;
+                        uint32_t       w, len;
+                        if (code < 12u) { len = (code >> 2) + 2u; w = 2u; }
+                        else            { len = code - 7u;        w = 4u; }
+                        if (avail < hdr) {
+                            done = true;
+                        } else if (o == 0u) {
+                            if (is_short) done = true;  /* end marker */
+                            else need = 13u;            /* long offset 0: no length field */
+                        } else if (avail < hdr + w) {
+                            done = true;
+                        } else {
+                            need = hdr + w;
+                            L = len;
+                            off = o;
+                            ext = (len == kMaxShortLen);
+                        }
+                    }
+                } else {                                /* 4-bit continuation */
+                    if (avail < 4u) {
+                        done = true;
+                    } else {
+                        need = 4u;
+                        L = top >> 28;
+                        ext = (L == kMaxExtLen);
+                    }
+                }
+                if (done) {
+                    L = 0;
+                } else {
+                    win <<= need;
+                    nb -= static_cast<int>(need);
+                    avail -= need;
+                    L = umin32(L, cap - pos);
+                }
+            }
+        }
+
+        /* ---- copy: read everything, then write (the ring is one byte larger than the
+         * window, so byte k+1 lands on the slot byte k reads at offset 2047) ---- */
+        uint8_t v[kPass];
+#pragma unroll
+        for (int t = 0; t < kPass; t++) {
+            const uint32_t k = gl + static_cast<uint32_t>(t) * G;
+            v[t] = static_cast<uint8_t>(lit_byte);
+            if (!lit && k < L) {
+                uint32_t kk = k;
+                if (kk >= off) kk %= off;               /* overlap: periodic extension */
+                const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
+                v[t] = (s >= 0) ? ring[static_cast<uint32_t>(s) & (kDecRing - 1u)] : 0;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < kPass; t++) {
+            const uint32_t k = gl + static_cast<uint32_t>(t) * G;
+            if (k < L) ring[(pos + k) & (kDecRing - 1u)] = v[t];
+        }
+        pos += L;
+        __syncwarp();
+
+        if (active && pos - flushed >= 16u * G) {
+            const uint32_t p = flushed + 16u * gl;
+            if (vec_ok) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(ring + (p & (kDecRing - 1u)));
+                *reinterpret_cast<uint4 *>(dst + p) = q;
+            } else {
+                for (uint32_t b = 0; b < 16u; b++) dst[p + b] = ring[(p + b) & (kDecRing - 1u)];
+            }
+            flushed += 16u * G;
+        }
+        if (active && done) {
+            for (uint32_t k = flushed + gl; k < pos; k += G) dst[k] = ring[k & (kDecRing - 1u)];
+            if (gl == 0) out_len[sid] = pos;
+            active = false;
+        }
     }
 }
 

@@ -59,6 +59,27 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t *p, const uint
     return __funnelshift_r(lo, hi, sh);
 }
 
+/* Named barriers (PTX bar.sync / bar.arrive): `count` threads take part in total;
+ * sync waits for all of them, arrive only signals.  Used for producer/consumer
+ * hand-off between warp groups of one CTA. */
+__device__ __forceinline__ void named_sync(int id, unsigned count)
+{
+#ifdef LZS_SIMT_EMU
+    simt_named_barrier_sync(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void named_arrive(int id, unsigned count)
+{
+#ifdef LZS_SIMT_EMU
+    simt_named_barrier_arrive(id, count);
+#else
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 }  // namespace lzs
 
 #endif /* LZS_B200_COMMON_CUH */

@@ -161,6 +161,17 @@ static inline void simt_named_barrier_sync(int id, unsigned nthreads)
     }
 }
 
+/* bar.arrive id, nthreads: count towards the barrier without waiting */
+static inline void simt_named_barrier_arrive(int id, unsigned nthreads)
+{
+    simt::Block *b = simt::g_block;
+    auto        &e = b->named[id];
+    if (++e.first == nthreads) {
+        e.first = 0;
+        e.second++;
+    }
+}
+
 static inline void simt_yield() { simt::yield(); }
 
 template <typename T>
