@@ -89,6 +89,22 @@ int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, co
                                    const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
                                    uint32_t n_streams);
 
+/* ------------------------------------------------------------------------------
+ * Batch form of the incremental calls of lzs.h (reference lzs.h:222, :232): advance
+ * n independent caller-owned streams by ONE lzs_compress_incremental /
+ * lzs_decompress_incremental call each, in a single launch (one warp per stream).
+ * Each block is used exactly as for the single call: set inPtr/inLength/outPtr/
+ * outLength before, read them and `status` after.  produced[s] (may be NULL) is what
+ * the single call would have returned.  For whole packets (init, then one call with
+ * add_end_marker until LZS_C_STATUS_END_MARKER) lzs_b200_compress_batch_* gives the
+ * same bytes and is much faster.
+ * ---------------------------------------------------------------------------- */
+#ifdef LZS_B200_LZS_H
+int lzs_b200_compress_incremental_batch(LzsCompressParameters_t **params, uint32_t n, int add_end_marker,
+                                        size_t *produced);
+int lzs_b200_decompress_incremental_batch(LzsDecompressParameters_t **params, uint32_t n, size_t *produced);
+#endif
+
 /* Uniform chunking helpers (host arrays): stream s covers [s*chunk, min((s+1)*chunk, total))
  * and its output slot starts at s*out_stride. */
 uint32_t lzs_b200_chunk_count(uint64_t total, uint32_t chunk);

@@ -54,3 +54,40 @@ extern "C" int emu_parse_pack(const uint8_t *in, const uint64_t *in_off, const u
     });
     return 0;
 }
+
+#include "../../lzs-compression_b200/csrc/incremental.cuh"
+
+/* One incremental call on the emulator.  `state` is the caller's private state block
+ * (host memory stands in for device memory here). */
+extern "C" int emu_inc_call(int decompress, void *state, const uint8_t *in, uint32_t in_len, uint8_t *out,
+                            uint32_t out_cap, int add_end_marker, uint32_t *in_used, uint32_t *out_used,
+                            uint32_t *status)
+{
+    lzs::IncJob job;
+    job.state = state;
+    job.in = in;
+    job.out = out;
+    job.in_len = in_len;
+    job.out_cap = out_cap;
+    job.in_used = job.out_used = job.status = 0;
+    job.add_end_marker = add_end_marker ? 1u : 0u;
+    simt::launch(dim3(1), dim3(128), 0, [&] {
+        if (decompress) lzs::kinc_decompress(&job, 1);
+        else            lzs::kinc_compress(&job, 1);
+    });
+    *in_used = job.in_used;
+    *out_used = job.out_used;
+    *status = job.status;
+    return 0;
+}
+
+extern "C" void emu_inc_init(int decompress, void *state)
+{
+    if (decompress) {
+        lzs::IncDecompressState *s = static_cast<lzs::IncDecompressState *>(state);
+        memset(s, 0, offsetof(lzs::IncDecompressState, ring));
+        s->state = lzs::kDTokenType;
+    } else {
+        memset(state, 0, offsetof(lzs::IncCompressState, ring));
+    }
+}

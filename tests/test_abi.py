@@ -1,0 +1,96 @@
+"""The drop-in boundary without a GPU: liblzs.so loads, exports every function that
+include/lzs.h and include/lzs_b200.h declare, keeps the reference's struct sizes, and
+fails loudly (never falls back to CPU code) when no CUDA device is present."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from gpu_common import binding
+
+INCLUDE = os.path.join(helpers.ROOT, "include")
+
+
+def _declared_functions(path):
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"static inline[^{]*\{.*?\n\}", "", text, flags=re.S)
+    text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))
+    return sorted(set(re.findall(r"\b(lzs_\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def B():
+    b = binding()
+    if not os.path.exists(b.LIB_PATH):
+        b.build()
+    return b
+
+
+def test_library_exports_every_declared_symbol(B):
+    L = B.lib()
+    names = _declared_functions(os.path.join(INCLUDE, "lzs.h")) + _declared_functions(os.path.join(INCLUDE, "lzs_b200.h"))
+    assert len(names) >= 25
+    for ref_name in ("lzs_compress", "lzs_compress_init_quick", "lzs_compress_init_full", "lzs_compress_incremental",
+                     "lzs_simple_compress", "lzs_simple_compress_init", "lzs_simple_compress_incremental",
+                     "lzs_decompress", "lzs_decompress_init", "lzs_decompress_incremental"):
+        assert ref_name in names                       # the ten reference entry points, lzs.h:218-232
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_headers_compile_as_c_and_keep_reference_struct_sizes(tmp_path):
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lzs.h"\n#include "lzs_b200.h"\n'
+                   'int main(void){ LzsCompressParameters_t p; lzs_compress_init; (void)p;\n'
+                   'printf("%zu %zu %zu %zu %zu %u %u\\n", sizeof(LzsCompressParameters_t), '
+                   'sizeof(LzsSimpleCompressParameters_t), sizeof(LzsDecompressParameters_t), '
+                   'offsetof(LzsCompressParameters_t, status), offsetof(LzsDecompressParameters_t, outLength), '
+                   '(unsigned)LZS_COMPRESSED_MAX(65536u), (unsigned)LZS_DECOMPRESSED_MAX(10u)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-unused-value", "-I", INCLUDE, str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["14432", "2112", "2096", "32", "24", "73731", "160"]
+
+
+def test_no_cpu_fallback_without_a_device(B):
+    """On a box without a GPU every entry point must report failure, not compute on the CPU."""
+    L = B.lib()
+    if L.lzs_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(B.LzsError):
+        B.compress_streams([b"hello hello hello"])
+    assert b"no CUDA device" in L.lzs_b200_last_error() or b"failed" in L.lzs_b200_last_error()
+    assert B.lzs_compress(b"hello hello hello") == b""              # 0 bytes + stderr diagnostic
+    assert B.lzs_decompress(bytes([0xC0, 0x00]), 16) == b""
+
+
+def test_product_never_links_the_oracle(B):
+    out = subprocess.run(["ldd", B.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "lzs_ref" not in out
+    srcs = []
+    for root, _, files in os.walk(os.path.join(helpers.ROOT, "lzs-compression_b200")):
+        srcs += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".py"))]
+    for s in srcs:
+        text = open(s).read()
+        assert "oracle/" not in text and "liblzs_oracle" not in text and "liblzs_ref" not in text, s
+
+
+def test_chunk_layout_helper(B):
+    L = B.lib()
+    total, chunk, stride = 200000, 65536, 73744
+    n = L.lzs_b200_chunk_count(total, chunk)
+    assert n == 4
+    in_off = np.zeros(n, dtype=np.uint64); in_len = np.zeros(n, dtype=np.uint32)
+    out_off = np.zeros(n, dtype=np.uint64); out_cap = np.zeros(n, dtype=np.uint32)
+    L.lzs_b200_chunk_layout.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, B.u64p, B.u32p, B.u64p, B.u32p]
+    L.lzs_b200_chunk_layout(total, chunk, stride, B._p(in_off, B.u64p), B._p(in_len, B.u32p), B._p(out_off, B.u64p),
+                            B._p(out_cap, B.u32p))
+    assert list(in_off) == [0, 65536, 131072, 196608] and list(in_len) == [65536, 65536, 65536, 3392]
+    assert list(out_off) == [0, stride, 2 * stride, 3 * stride] and set(out_cap) == {stride}

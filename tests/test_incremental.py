@@ -1,0 +1,152 @@
+"""Incremental API parity: every call's (return value, status flags, input consumed) and
+the concatenated bytes must equal the unmodified reference's for any slicing of input
+and output (reference tests c/src/test/test-lzs-decompression.c:130-290 do this for the
+decoder with 10-byte slices; the compressor's incremental API has no reference test).
+
+CPU part: the product's device state machines (csrc/incremental.cuh) on the SIMT
+emulator.  GPU part (-m gpu): the same calls through liblzs.so."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import emu
+import helpers
+import inc_drivers as D
+from gpu_common import binding
+
+SLICINGS_C = [(1 << 20, 1 << 20), (7, 5), (512, 512), (1, 3), (1500, 3), (13, 1 << 20)]
+SLICINGS_D = [(1 << 20, 1 << 20), (10, 1 << 20), (1 << 20, 10), (3, 7), (1, 1)]
+
+
+def _ref():
+    if not os.path.exists(helpers.REF_SO):
+        pytest.skip("oracle/_ref/liblzs_ref.so not built")
+    return ctypes.CDLL(helpers.REF_SO)
+
+
+def _inputs():
+    cases = helpers.edge_case_inputs()
+    keep = ["empty", "one", "two_same", "run_38", "abab", "tail_short", "period_2047", "records"]
+    data = {k: cases[k] for k in keep}
+    data["packet"] = helpers.corpus(helpers.CORPUS_PACKET, 1, 1500).tobytes()
+    data["text_5000"] = helpers.corpus(helpers.CORPUS_TEXT, 1, 5000).tobytes()
+    data["run_5000"] = b"\0" * 5000
+    return data
+
+
+def _check_compress(ours, ref, data, i_s, o_s, **kw):
+    cap = helpers.compressed_max(len(data)) + 8
+    a, ta = D.drive(ref, False, data, i_s, o_s, cap, **kw)
+    b, tb = D.drive(ours, False, data, i_s, o_s, cap, **kw)
+    assert tb == ta, "call traces differ"
+    assert b == a
+    return a
+
+
+def _check_decompress(ours, ref, stream, i_s, o_s, cap):
+    a, ta = D.drive(ref, True, stream, i_s, o_s, cap)
+    b, tb = D.drive(ours, True, stream, i_s, o_s, cap)
+    assert tb == ta, "call traces differ"
+    assert b == a
+    return a
+
+
+def test_emulated_incremental_compress_matches_reference_calls():
+    ref, ours, o = D.StructCodec(_ref()), D.EmuCodec(emu.lib()), helpers.oracle()
+    for name, data in _inputs().items():
+        for i_s, o_s in SLICINGS_C:
+            if len(data) > 2000 and i_s == 1:
+                continue
+            out = _check_compress(ours, ref, data, i_s, o_s)
+            assert out == o.compress(data), (name, i_s, o_s)
+
+
+def test_emulated_incremental_compress_without_end_marker():
+    """add_end_marker=false holds back the last <12 / <15 bytes (lzs-compression.c:641-647,
+    :750-758); the emitted prefix must still agree call for call."""
+    ref, ours = D.StructCodec(_ref()), D.EmuCodec(emu.lib())
+    for name in ("packet", "run_38", "records"):
+        _check_compress(ours, ref, _inputs()[name], 100, 64, finish_last=False)
+
+
+def test_emulated_simple_variant_is_the_same_engine():
+    ref_simple, ours, o = D.StructCodec(_ref(), simple=True), D.EmuCodec(emu.lib()), helpers.oracle()
+    data = _inputs()["packet"]
+    assert _check_compress(ours, ref_simple, data, 64, 64) == o.compress(data)
+
+
+def test_emulated_incremental_decompress_matches_reference_calls():
+    ref, ours, o = D.StructCodec(_ref()), D.EmuCodec(emu.lib()), helpers.oracle()
+    golden = open(os.path.join(helpers.GOLDEN_DIR, "golden1_compressed.bin"), "rb").read()
+    plain = open(os.path.join(helpers.GOLDEN_DIR, "golden1_plain.bin"), "rb").read()
+    for i_s, o_s in SLICINGS_D:                       # the reference's own four drivers, and more
+        assert _check_decompress(ours, ref, golden, i_s, o_s, len(plain) + 520) == plain
+    for name, data in _inputs().items():
+        stream = o.compress(data)
+        for i_s, o_s in SLICINGS_D[:4]:
+            assert _check_decompress(ours, ref, stream, i_s, o_s, len(data) + 16) == data, (name, i_s, o_s)
+    # concatenated streams: history is kept across end markers (lzs-decompression.c:564-576)
+    two = o.compress(b"hello hello hello ") + o.compress(b"world world")
+    _check_decompress(ours, ref, two, 5, 1 << 20, 100)
+    # truncated and noisy streams
+    rng = np.random.default_rng(3)
+    for k in range(6):
+        noise = rng.integers(0, 256, 120, dtype=np.uint8).tobytes()
+        _check_decompress(ours, ref, noise, 9, 50, 3000)
+
+
+@pytest.mark.gpu
+def test_gpu_incremental_matches_reference_calls():
+    B = binding()
+    ours, ref, o = D.StructCodec(B.lib()), D.StructCodec(_ref()), helpers.oracle()
+    ours_simple = D.StructCodec(B.lib(), simple=True)
+    inputs = _inputs()
+    for name in ("empty", "one", "run_38", "packet", "records"):
+        data = inputs[name]
+        for i_s, o_s in [(1 << 20, 1 << 20), (512, 512), (100, 3)]:
+            assert _check_compress(ours, ref, data, i_s, o_s) == o.compress(data)
+        assert _check_compress(ours, ref, data, 1 << 20, 1 << 20, quick=True) == o.compress(data)
+        assert _check_compress(ours_simple, ref, data, 300, 300) == o.compress(data)
+        _check_compress(ours, ref, data, 100, 64, finish_last=False)
+        stream = o.compress(data)
+        for i_s, o_s in [(1 << 20, 1 << 20), (10, 1 << 20), (1 << 20, 10)]:
+            assert _check_decompress(ours, ref, stream, i_s, o_s, len(data) + 16) == data
+
+
+@pytest.mark.gpu
+def test_gpu_incremental_batch_of_packets():
+    """BASELINE config 3 through the incremental API: init + incremental(add_end_marker=true)
+    until END_MARKER per packet, all packets advanced together, equals lzs_compress(packet)."""
+    B = binding()
+    L = B.lib()
+    o = helpers.oracle()
+    n, plen = 256, 1500
+    pk = helpers.corpus(helpers.CORPUS_PACKET, n, plen, seed=0x5EED0000 + 3)
+    cap = helpers.compressed_max(plen)
+    src = np.zeros(n * plen + 16, dtype=np.uint8)
+    src[:n * plen] = pk
+    dst = np.zeros(n * cap, dtype=np.uint8)
+    blocks = [ctypes.create_string_buffer(D.C_SIZE) for _ in range(n)]
+    L.lzs_compress_init_full.argtypes = [ctypes.c_void_p]
+    arr = (ctypes.c_void_p * n)()
+    for s, b in enumerate(blocks):
+        L.lzs_compress_init_full(b)
+        f = (ctypes.c_uint64 * 4).from_address(ctypes.addressof(b))
+        f[0], f[1], f[2], f[3] = src.ctypes.data + s * plen, dst.ctypes.data + s * cap, plen, cap
+        arr[s] = ctypes.addressof(b)
+    L.lzs_b200_compress_incremental_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+    for _ in range(64):
+        B.check(L.lzs_b200_compress_incremental_batch(arr, n, 1, None))
+        if all(ctypes.c_uint8.from_address(ctypes.addressof(b) + 32).value & D.END_MARKER for b in blocks):
+            break
+    else:
+        raise AssertionError("packets never reached END_MARKER")
+    for s, b in enumerate(blocks):
+        f = (ctypes.c_uint64 * 4).from_address(ctypes.addressof(b))
+        got = dst[s * cap:s * cap + (cap - f[3])].tobytes()
+        assert got == o.compress(pk[s * plen:(s + 1) * plen].tobytes()), s
+    # and the bulk path gives the same bytes (the fast way to do the same thing)
+    assert B.compress_streams([pk[s * plen:(s + 1) * plen].tobytes() for s in range(8)]) == \
+        [o.compress(pk[s * plen:(s + 1) * plen].tobytes()) for s in range(8)]
