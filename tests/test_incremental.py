@@ -137,9 +137,15 @@ def test_gpu_incremental_batch_of_packets():
         f[0], f[1], f[2], f[3] = src.ctypes.data + s * plen, dst.ctypes.data + s * cap, plen, cap
         arr[s] = ctypes.addressof(b)
     L.lzs_b200_compress_incremental_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
-    for _ in range(64):
-        B.check(L.lzs_b200_compress_incremental_batch(arr, n, 1, None))
-        if all(ctypes.c_uint8.from_address(ctypes.addressof(b) + 32).value & D.END_MARKER for b in blocks):
+    def done(b):
+        return ctypes.c_uint8.from_address(ctypes.addressof(b) + 32).value & D.END_MARKER
+
+    todo = list(blocks)
+    for _ in range(64):                               # like the caller's loop in utils/lzs-compress.c:91-134
+        arr = (ctypes.c_void_p * len(todo))(*[ctypes.addressof(b) for b in todo])
+        B.check(L.lzs_b200_compress_incremental_batch(arr, len(todo), 1, None))
+        todo = [b for b in todo if not done(b)]       # a stream stops being called at its end marker
+        if not todo:
             break
     else:
         raise AssertionError("packets never reached END_MARKER")
