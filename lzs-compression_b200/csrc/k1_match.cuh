@@ -41,11 +41,17 @@
  * Layout: one persistent CTA per SM (208 KiB of shared memory: 11 head tables,
  * 11 link rings, a ring of 4-byte grams), streams pulled from a global counter and
  * walked in 992-position tiles.  The CTA is warp specialised: 11 build warps (one
- * per level) run one tile ahead of 13 query warps; the two groups hand tiles over
+ * per level) run one tile ahead of 16 query warps; the two groups hand tiles over
  * through named barriers (double buffered).  Positions are numbered continuously
  * across the streams a CTA processes ("virtual positions"), so the rings need no
  * clearing between streams; a candidate is valid only if its distance does not
  * exceed the position inside the current stream.
+ *
+ * Tried and measured slower on B200 (see profiles/README.md): several levels per build
+ * warp (fewer instructions, but one warp's dependent-issue latency then bounds a batch),
+ * and a software-pipelined insert that takes the read-back off the critical path
+ * (lanes in reverse position order, because sm_100a lets the LOWEST lane win a
+ * shared-memory store conflict -- tools/micro/sts_winner.cu).
  *
  * Output: one uint16 per input byte, (len << 11) | offset, consumed by K2.
  * HBM traffic per input byte: 1 B read + 2 B written (intermediate).
@@ -64,7 +70,7 @@ constexpr uint32_t kK1WRing = 8192;
 constexpr uint32_t kK1Tile = 992;           /* 31 batches of 32                    */
 constexpr uint32_t kK1StreamGap = 16;       /* virtual positions between streams   */
 constexpr int      kK1BuildWarps = kK1Levels;
-constexpr int      kK1QueryWarps = 13;
+constexpr int      kK1QueryWarps = 16;
 constexpr int      kK1Threads = 32 * (kK1BuildWarps + kK1QueryWarps);
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;

@@ -128,7 +128,9 @@ k23_parse_pack(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
         const uint32_t byte = valid ? src[i] : 0u;
         const uint32_t len = mv >> kMatchOffBits;
         const uint32_t off = mv & ((1u << kMatchOffBits) - 1u);
-        const bool     is_long = len >= kMaxShortLen;
+        /* K1 caps lengths at 12: 8..11 are exact (one 4-bit continuation, known here);
+         * only 12 means "12 or more" and needs the bytes compared further */
+        const bool     is_long = len >= kSearchMax;
         const uint32_t nxt = lane + (len >= kMinLen ? len : 1u);
 
         /* K2: token starts reachable from lane 0 inside this group */
@@ -157,9 +159,14 @@ k23_parse_pack(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
                 if (len <= 4u) {
                     val = (val << 2) | (len - 2u);
                     nb += 2u;
-                } else {
-                    const uint32_t code = is_long ? 0xFu : (0xCu + len - 5u);
-                    val = (val << 4) | code;
+                } else if (len < kMaxShortLen) {
+                    val = (val << 4) | (0xCu + len - 5u);
+                    nb += 4u;
+                } else if (!is_long) {                        /* 8..11: 1111 + (len - 8) */
+                    val = (val << 8) | 0xF0u | (len - kMaxShortLen);
+                    nb += 8u;
+                } else {                                      /* >= 12: 1111, nibbles follow below */
+                    val = (val << 4) | 0xFu;
                     nb += 4u;
                 }
             }
@@ -184,7 +191,7 @@ k23_parse_pack(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
             /* true length of the long match that ended the group */
             const uint32_t p = pos + static_cast<uint32_t>(last);
             const uint32_t loff = __shfl_sync(LZS_FULL_MASK, off, last);
-            uint32_t       L = kMaxShortLen;
+            uint32_t       L = kSearchMax;                    /* the first 12 bytes are known to match */
             for (;;) {
                 const uint32_t idx = p + L + lane;
                 const bool     same = (idx < n) && (src[idx] == src[idx - loff]);

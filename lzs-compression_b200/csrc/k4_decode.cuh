@@ -12,8 +12,12 @@
  * Mapping: G lanes of a warp decode one stream (G = 4/8/16/32), so one warp
  * instruction serves 32/G streams.  The token parse is inherently serial per
  * stream, so the lanes of a group run it redundantly and split the back-reference
- * copy.  All 32/G groups of a warp advance in lock step, one token per iteration,
- * under warp-uniform control flow: every collective uses the full mask (a
+ * copy.  All 32/G groups of a warp advance in lock step under warp-uniform control
+ * flow; one step takes a run of up to 7 literals (lane g looks at the token that
+ * would start 9*g bits after the cursor; a ballot gives the length of the run) and
+ * then at most one match or continuation token.  The bit stream is read through a
+ * 4-word register cache (96 bits visible from the cursor).  Every collective uses
+ * the full mask (a
  * variable member mask makes nvcc emit MATCH.ANY, ~50-390 cycles on sm_100a), and
  * a group whose stream ended simply idles until it has fetched the next stream
  * index from a global counter (which also balances incompressible vs. text chunks).
@@ -63,14 +67,17 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     LZS_DYN_SMEM(uint8_t, smem);
     const uint32_t lane = lane_id();
     const uint32_t gl = lane % G;
+    const uint32_t gshift = lane - gl;                  /* first lane of my group            */
     uint8_t *ring = smem + static_cast<size_t>(threadIdx.x / G) * kDecRing;
-    constexpr int kPass = (static_cast<int>(kMaxExtLen) + G - 1) / G;
+    constexpr int      kPass = (static_cast<int>(kMaxExtLen) + G - 1) / G;
+    constexpr uint32_t kMaxLit = G < 7 ? G : 7;         /* literals per step: 9 * 7 <= 64 bits */
+    constexpr uint32_t kGroupBits = (G == 32) ? 0xFFFFFFFFu : ((1u << (G & 31)) - 1u);
 
     /* per-stream state; identical in all lanes of a group */
     bool     active = false, exhausted = false, ext = false, vec_ok = false;
-    uint32_t sid = 0, cap = 0, pos = 0, flushed = 0, off = 1, wi = 0, nextw = 0;
-    int      nb = 0;
-    uint64_t win = 0, avail = 0;
+    uint32_t sid = 0, cap = 0, pos = 0, flushed = 0, off = 1;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, wbase = 0; /* stream words [wbase, wbase+4)     */
+    uint64_t cur = 0, end = 0;                          /* bit cursor / end, from word 0      */
     uint8_t *dst = nullptr;
     DecInput src{nullptr, 0, 0};
 
@@ -96,12 +103,10 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     dst = out + out_off[sid];
                     cap = out_cap[sid];
                     vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
-                    avail = static_cast<uint64_t>(nin) * 8u;
-                    /* the `lead` bytes before the stream inside its first word are skipped */
-                    win = static_cast<uint64_t>(src.fetch(0)) << (32u + 8u * lead);
-                    nb = 32 - static_cast<int>(8u * lead);
-                    nextw = src.fetch(1);
-                    wi = 2;
+                    cur = 8u * lead;                    /* bytes before the stream in word 0 */
+                    end = cur + static_cast<uint64_t>(nin) * 8u;
+                    wbase = 0;
+                    w0 = src.fetch(0); w1 = src.fetch(1); w2 = src.fetch(2); w3 = src.fetch(3);
                     pos = 0;
                     flushed = 0;
                     off = 1;
@@ -112,81 +117,94 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
         }
         if (__all_sync(LZS_FULL_MASK, !active)) break;
 
-        /* ---- one token per active group ---- */
-        bool     done = false, lit = false;
-        uint32_t L = 0, lit_byte = 0;
-        if (active) {
-            if (avail == 0 || pos >= cap) {
-                done = true;
-            } else {
-                if (nb <= 32) {
-                    win |= static_cast<uint64_t>(nextw) << (32 - nb);
-                    nb += 32;
-                    nextw = src.fetch(wi++);
-                }
-                const uint32_t top = static_cast<uint32_t>(win >> 32);
-                uint32_t       need = 0;
-                if (!ext) {
-                    if ((top >> 31) == 0u) {            /* literal: 0 + 8 bits */
-                        need = 9u;
-                        lit_byte = (top >> 23) & 0xFFu;
-                        L = 1u;
-                        lit = true;
-                        if (avail < need) done = true;
-                    } else {
-                        const uint32_t is_short = (top >> 30) & 1u;
-                        const uint32_t hdr = is_short ? 9u : 13u;
-                        const uint32_t o = is_short ? ((top >> 23) & 0x7Fu) : ((top >> 19) & 0x7FFu);
-                        const uint32_t code = (top << hdr) >> 28;
-                        uint32_t       w, len;
-                        if (code < 12u) { len = (code >> 2) + 2u; w = 2u; }
-                        else            { len = code - 7u;        w = 4u; }
-                        if (avail < hdr) {
-                            done = true;
-                        } else if (o == 0u) {
-                            if (is_short) done = true;  /* end marker */
-                            else need = 13u;            /* long offset 0: no length field */
-                        } else if (avail < hdr + w) {
-                            done = true;
-                        } else {
-                            need = hdr + w;
-                            L = len;
-                            off = o;
-                            ext = (len == kMaxShortLen);
-                        }
-                    }
-                } else {                                /* 4-bit continuation */
-                    if (avail < 4u) {
-                        done = true;
-                    } else {
-                        need = 4u;
-                        L = top >> 28;
-                        ext = (L == kMaxExtLen);
-                    }
-                }
-                if (done) {
-                    L = 0;
-                } else {
-                    win <<= need;
-                    nb -= static_cast<int>(need);
-                    avail -= need;
-                    L = umin32(L, cap - pos);
-                }
+        /* ---- 96 bits of the stream starting at the cursor ---- */
+        {
+            const uint32_t wi = static_cast<uint32_t>(cur >> 5);
+            while (active && wbase < wi) {
+                w0 = w1; w1 = w2; w2 = w3;
+                w3 = src.fetch(wbase + 4u);
+                wbase++;
             }
         }
+        const uint32_t sh = static_cast<uint32_t>(cur) & 31u;
+        const uint32_t b0 = __funnelshift_l(w1, w0, sh);
+        const uint32_t b1 = __funnelshift_l(w2, w1, sh);
+        const uint32_t b2 = __funnelshift_l(w3, w2, sh);
+        const uint64_t left = end - cur;
+        uint32_t       avail = left > 0xFFFFu ? 0xFFFFu : static_cast<uint32_t>(left);
 
-        /* ---- copy: read everything, then write (the ring is one byte larger than the
-         * window, so byte k+1 lands on the slot byte k reads at offset 2047) ---- */
+        /* ---- phase A: a run of literals, one per lane (token gl starts at bit 9*gl) ---- */
+        uint32_t nlit = 0;
+        {
+            const uint32_t at = 9u * gl;                /* < 64 for gl < 7                    */
+            const uint64_t b01 = (static_cast<uint64_t>(b0) << 32) | b1;
+            const uint32_t field = static_cast<uint32_t>((b01 << (at & 63u)) >> 55);   /* 9 bits */
+            const bool     is_lit = active && !ext && gl < kMaxLit && (field >> 8) == 0u &&
+                                avail >= at + 9u && pos + gl < cap;
+            const uint32_t mine = (__ballot_sync(LZS_FULL_MASK, is_lit) >> gshift) & kGroupBits;
+            nlit = static_cast<uint32_t>(__ffs(static_cast<int>(~mine))) - 1u;          /* leading literals */
+            if (gl < nlit) ring[(pos + gl) & (kDecRing - 1u)] = static_cast<uint8_t>(field);
+        }
+        pos += nlit;
+        avail -= 9u * nlit;
+        uint32_t used = 9u * nlit;                      /* bits consumed this step            */
+        __syncwarp();
+
+        /* ---- phase B: at most one match / continuation token ---- */
+        bool     done = false;
+        uint32_t L = 0;
+        if (active) {
+            const uint32_t top = used < 32u ? __funnelshift_l(b1, b0, used) : __funnelshift_l(b2, b1, used - 32u);
+            if (avail == 0u || pos >= cap) {
+                done = true;
+            } else if (ext) {                           /* 4-bit continuation */
+                if (avail < 4u) {
+                    done = true;
+                } else {
+                    used += 4u;
+                    L = top >> 28;
+                    ext = (L == kMaxExtLen);
+                }
+            } else if ((top >> 31) == 0u) {             /* a literal phase A could not take   */
+                if (avail < 9u) done = true;            /* (8th in a row: next step)          */
+            } else {
+                const uint32_t is_short = (top >> 30) & 1u;
+                const uint32_t hdr = is_short ? 9u : 13u;
+                const uint32_t o = is_short ? ((top >> 23) & 0x7Fu) : ((top >> 19) & 0x7FFu);
+                const uint32_t code = (top << hdr) >> 28;
+                uint32_t       w, len;
+                if (code < 12u) { len = (code >> 2) + 2u; w = 2u; }
+                else            { len = code - 7u;        w = 4u; }
+                if (avail < hdr) {
+                    done = true;
+                } else if (o == 0u) {
+                    if (is_short) done = true;          /* end marker */
+                    else used += 13u;                   /* long offset 0: no length field */
+                } else if (avail < hdr + w) {
+                    done = true;
+                } else {
+                    used += hdr + w;
+                    L = len;
+                    off = o;
+                    ext = (len == kMaxShortLen);
+                }
+            }
+            L = umin32(L, cap - pos);
+            cur += used;
+        }
+
+        /* copy: read everything, then write (the ring is one byte larger than the window,
+         * so byte k+1 lands on the slot byte k reads at offset 2047) */
         uint8_t v[kPass];
 #pragma unroll
         for (int t = 0; t < kPass; t++) {
             const uint32_t k = gl + static_cast<uint32_t>(t) * G;
-            v[t] = static_cast<uint8_t>(lit_byte);
-            if (!lit && k < L) {
+            v[t] = 0;
+            if (k < L) {
                 uint32_t kk = k;
                 if (kk >= off) kk %= off;               /* overlap: periodic extension */
                 const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
-                v[t] = (s >= 0) ? ring[static_cast<uint32_t>(s) & (kDecRing - 1u)] : 0;
+                if (s >= 0) v[t] = ring[static_cast<uint32_t>(s) & (kDecRing - 1u)];
             }
         }
         __syncwarp();
