@@ -230,6 +230,23 @@ def run_gpu_arm(args):
     assert db.roundtrip_ok(), "round trip mismatch inside the timed region"
     comp_bytes = db.compressed_bytes()
 
+    # ---- optional exchange step (N > 1): all-gather-v of the variable-size outputs over NCCL,
+    #      timed separately -- it is not part of the data path
+    gather = None
+    if dist is not None:
+        import lzs_dist
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(2):
+            barrier()
+            g0.record()
+            packed = lzs_dist.pack_streams(db.comp, db.comp_off, db.comp_len)
+            payload, lens, offs = lzs_dist.all_gather_streams(packed, db.comp_len)
+            g1.record()
+            torch.cuda.synchronize()
+        gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank_received": int(payload.numel()),
+                  "streams": int(lens.numel()), "what": "pack + all-gather-v of compressed streams to every rank (NCCL)"}
+        assert int(lens.numel()) == n_chunks * world and int(payload.numel()) == int(lens.sum().item())
+
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -268,6 +285,8 @@ def run_gpu_arm(args):
             line["e2e"] = {"value": job_bytes / (t_e2e * 1e-3) / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "steps": e2e["steps"], "api": "lzs_b200_compress_batch_host + lzs_b200_decompress_batch_host"}
+        if gather:
+            line["gather"] = gather
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(db)
         print(json.dumps(line))
