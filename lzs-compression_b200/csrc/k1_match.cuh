@@ -67,7 +67,10 @@ constexpr int      kK1Levels = 11;          /* k = 2 .. 12 */
 constexpr uint32_t kK1Slots = 4096;
 constexpr uint32_t kK1LinkRing = 4096;      /* >= 2047 + 2 * (tile + gap)          */
 constexpr uint32_t kK1WRing = 8192;
-constexpr uint32_t kK1Tile = 992;           /* 31 batches of 32                    */
+#ifndef LZS_K1_TILE
+#define LZS_K1_TILE 992
+#endif
+constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 992 = 31 batches  */
 constexpr uint32_t kK1StreamGap = 16;       /* virtual positions between streams   */
 constexpr int      kK1BuildWarps = kK1Levels;
 constexpr int      kK1QueryWarps = 16;
@@ -77,6 +80,7 @@ constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
 constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 +
                                 static_cast<size_t>(kK1Levels) * kK1LinkRing * 2 + kK1WRing * 4;
 static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
+static_assert(kWindow + 3 * (kK1Tile + kK1StreamGap) + 16 < kK1WRing, "gram ring must hold one tile more than the links");
 
 enum { kBarBuild = 1, kBarFull0 = 2, kBarFull1 = 3, kBarEmpty0 = 4, kBarEmpty1 = 5 };
 constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
@@ -272,13 +276,15 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
 
             for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
                 const uint32_t buf = g & 1u;
-                if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
                 const uint32_t tile_n = umin32(kK1Tile, n - t0);
-                /* 4-byte grams of the new positions (+8 look-ahead for 12-byte compares) */
+                /* 4-byte grams of the new positions (+8 look-ahead for 12-byte compares).  Done
+                 * BEFORE waiting for the query group: the gram ring is large enough that these
+                 * slots are free, so the global-load latency hides in that wait. */
                 const uint32_t p_lo = (t0 == 0) ? 0u : t0 + 8u;
                 const uint32_t p_hi = umin32(t0 + kK1Tile + 8u, n + 12u);
                 for (uint32_t p = p_lo + tid; p < p_hi; p += kK1BuildThreads)
                     W[(v0 + p) & (kK1WRing - 1)] = (p < n) ? load4_unaligned(src + p, end) : 0u;
+                if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
                 named_sync(kBarBuild, kK1BuildThreads);
 
                 switch (warp) {
