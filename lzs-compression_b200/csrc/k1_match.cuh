@@ -38,10 +38,10 @@
  *   candidate at level l, so the next level tried is l + 1, and the first level
  *   without a candidate ends the search.
  *
- * Layout: one persistent CTA per SM (208 KiB of shared memory: 11 head tables,
- * 11 link rings, a ring of 4-byte grams), streams pulled from a global counter and
- * walked in 992-position tiles.  The CTA is warp specialised: 11 build warps (one
- * per level) run one tile ahead of 16 query warps; the two groups hand tiles over
+ * Layout: one persistent CTA per SM (216 KiB of shared memory: 11 head tables,
+ * 11 link rings, the run table, a ring of 4-byte grams), streams pulled from a global counter and
+ * walked in 992-position tiles.  The CTA is warp specialised: 12 build warps (one
+ * per level plus the run table) run one tile ahead of 16 query warps; the two groups hand tiles over
  * through named barriers (double buffered).  Positions are numbered continuously
  * across the streams a CTA processes ("virtual positions"), so the rings need no
  * clearing between streams; a candidate is valid only if its distance does not
@@ -72,13 +72,15 @@ constexpr uint32_t kK1WRing = 8192;
 #endif
 constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 992 = 31 batches  */
 constexpr uint32_t kK1StreamGap = 16;       /* virtual positions between streams   */
-constexpr int      kK1BuildWarps = kK1Levels;
+constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the run-table warp */
 constexpr int      kK1QueryWarps = 16;
 constexpr int      kK1Threads = 32 * (kK1BuildWarps + kK1QueryWarps);
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
 constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 +
-                                static_cast<size_t>(kK1Levels) * kK1LinkRing * 2 + kK1WRing * 4;
+                                static_cast<size_t>(kK1Levels + 1) * kK1LinkRing * 2 + kK1WRing * 4;
+/* run table entry: (forward run length capped at 12) << 12 | distance back to the run start */
+constexpr uint32_t kRunBackMask = 0xFFFu;
 static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
 static_assert(kWindow + 3 * (kK1Tile + kK1StreamGap) + 16 < kK1WRing, "gram ring must hold one tile more than the links");
 
@@ -193,14 +195,48 @@ __device__ __forceinline__ void k1_build_level(uint16_t *heads, uint16_t *links,
     }
 }
 
+/* Run table of one tile (one whole warp).  For every position p it records how far back
+ * the run of identical bytes containing p starts (0 = p starts a run, capped at 4095)
+ * and how many identical bytes follow from p (capped at 12).  Positions p-1 and p have the
+ * same k-gram whenever the forward run at p-1 covers k+1 bytes, so inside a run of one
+ * byte value every level's chain visits the run members one by one; the table lets a
+ * query hop over all of them at once (see k1_query). */
+__device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W, uint32_t v0, uint32_t t0,
+                                              uint32_t tile_n)
+{
+    const uint32_t lane = lane_id();
+    for (uint32_t b = 0; b < tile_n; b += 32) {
+        const uint32_t i = t0 + b + lane;
+        const uint32_t v = v0 + i;
+        const bool     act = (b + lane) < tile_n;
+        const uint32_t w0 = W[v & (kK1WRing - 1)], w1 = W[(v + 4) & (kK1WRing - 1)], w2 = W[(v + 8) & (kK1WRing - 1)];
+        const uint32_t rep = (w0 & 0xFFu) * 0x01010101u;
+        const uint32_t fwd = lcp12(w0, w1, w2, rep, rep, rep);                 /* 1..12 */
+        const uint32_t prev = (i == 0) ? 0x100u : (W[(v - 1) & (kK1WRing - 1)] & 0xFFu);   /* byte i-1 */
+        const bool     start = !act || prev != (w0 & 0xFFu);                   /* p begins a run */
+        const uint32_t starts = __ballot_sync(LZS_FULL_MASK, start);
+        const uint32_t below = starts & ((2u << lane) - 1u);                   /* starts at or below my lane */
+        uint32_t       back;
+        if (below) {
+            back = lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(below))));
+        } else {                                                               /* the run began in an earlier batch */
+            const uint32_t carry = runs[(v0 + t0 + b - 1u) & (kK1LinkRing - 1)] & kRunBackMask;
+            back = umin32(carry + lane + 1u, kRunBackMask);
+        }
+        __syncwarp();
+        if (act) runs[v & (kK1LinkRing - 1)] = static_cast<uint16_t>((fwd << 12) | back);
+        __syncwarp();
+    }
+}
+
 /* One query = a single flat loop of chain steps (no nested loops, so lanes of a warp
  * stay together).  Levels are tried upwards: a verified candidate of length l at level
  * k answers every level up to l, so the next level tried is l + 1, and the first level
  * whose chain ends without a verified candidate ends the search ("some candidate
  * reaches k" is monotone in k).  Every chain link carries the 5-bit tag of the entry
  * it belongs to, so a foreign entry costs one shared-memory load. */
-__device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint32_t *W, uint32_t v0,
-                                             uint32_t i, uint32_t n)
+__device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16_t *runs, const uint32_t *W,
+                                             uint32_t v0, uint32_t i, uint32_t n)
 {
     const uint32_t M = umin32(kSearchMax, n - i);
     const uint32_t maxd = umin32(kWindow, i);
@@ -222,7 +258,20 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint32
         const uint32_t j = v - tot;
         e = lk[j & (kK1LinkRing - 1)];
         d = e & kLinkDistMask;
-        if ((e >> 11) != tag) continue;                      /* foreign entry of this slot  */
+        if ((e >> 11) != tag) {                              /* foreign entry of this slot  */
+            if (d == 1u) {
+                /* its predecessor is the adjacent position: if j sits inside a run of one
+                 * byte value that covers k bytes from j, every run member before j has j's
+                 * gram (not ours) and is the next entry of this chain -- skip to the run start */
+                const uint32_t r = runs[j & (kK1LinkRing - 1)];
+                const uint32_t back = r & kRunBackMask;
+                if ((r >> 12) >= k && back != 0u) {
+                    tot += back;
+                    d = lk[(j - back) & (kK1LinkRing - 1)] & kLinkDistMask;
+                }
+            }
+            continue;
+        }
         const uint32_t l = umin32(lcp12(w0, w1, w2, W[j & (kK1WRing - 1)], W[(j + 4) & (kK1WRing - 1)],
                                         W[(j + 8) & (kK1WRing - 1)]), M);
         if (l < k) continue;
@@ -247,14 +296,15 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     LZS_DYN_SMEM(uint8_t, smem);
     uint16_t *heads = reinterpret_cast<uint16_t *>(smem);
     uint16_t *links = heads + kK1Levels * kK1Slots;
-    uint32_t *W = reinterpret_cast<uint32_t *>(links + kK1Levels * kK1LinkRing);
+    uint16_t *runs = links + kK1Levels * kK1LinkRing;
+    uint32_t *W = reinterpret_cast<uint32_t *>(runs + kK1LinkRing);
     __shared__ uint32_t s_sid;
     __shared__ K1Tile   s_tile[2];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
 
-    for (uint32_t x = tid; x < kK1Levels * (kK1Slots + kK1LinkRing); x += kK1Threads) heads[x] = 0;
+    for (uint32_t x = tid; x < kK1Levels * (kK1Slots + kK1LinkRing) + kK1LinkRing; x += kK1Threads) heads[x] = 0;
     __syncthreads();
 
     if (warp < static_cast<uint32_t>(kK1BuildWarps)) {
@@ -298,7 +348,8 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     case 7:  k1_build_level<9>(heads, links, W, v0, t0, tile_n); break;
                     case 8:  k1_build_level<10>(heads, links, W, v0, t0, tile_n); break;
                     case 9:  k1_build_level<11>(heads, links, W, v0, t0, tile_n); break;
-                    default: k1_build_level<12>(heads, links, W, v0, t0, tile_n); break;
+                    case 10: k1_build_level<12>(heads, links, W, v0, t0, tile_n); break;
+                    default: k1_build_runs(runs, W, v0, t0, tile_n); break;
                 }
                 if (tid == 0) {
                     K1Tile d;
@@ -323,7 +374,7 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             match_t *mout = matches + in_off[d.sid];
             for (uint32_t r = qtid; r < d.tile_n; r += kK1QueryThreads) {
                 const uint32_t i = d.t0 + r;
-                mout[i] = static_cast<match_t>(k1_query(links, W, d.v0, i, d.n));
+                mout[i] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
             }
             named_arrive(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
         }
