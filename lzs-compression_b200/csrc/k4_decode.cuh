@@ -15,8 +15,11 @@
  * copy.  All 32/G groups of a warp advance in lock step under warp-uniform control
  * flow; one step takes a run of up to 7 literals (lane g looks at the token that
  * would start 9*g bits after the cursor; a ballot gives the length of the run) and
- * then at most one match or continuation token.  The bit stream is read through a
- * 4-word register cache (96 bits visible from the cursor).  Every collective uses
+ * then at most one match or continuation token, and a step repeats that three times
+ * before it pays the fixed costs (votes, refill and flush checks) again.  The
+ * compressed stream is staged in shared memory (64 words per stream, refilled 32
+ * words at a time well ahead of the cursor), so a bit field at any position is two
+ * shared-memory loads and a funnel shift.  Every collective uses
  * the full mask (a
  * variable member mask makes nvcc emit MATCH.ANY, ~50-390 cycles on sm_100a), and
  * a group whose stream ended simply idles until it has fetched the next stream
@@ -38,24 +41,13 @@
 namespace lzs {
 
 constexpr int      kDecThreads = 128;
-constexpr uint32_t kDecRing = 2048;
+constexpr uint32_t kDecRing = 2048;                 /* history bytes per stream             */
+constexpr uint32_t kDecInWords = 64;                /* staged input words per stream        */
+constexpr uint32_t kDecStreamSmem = kDecRing + 4 * kDecInWords;
+constexpr int      kDecRounds = 3;                  /* (literal run + one token) per step   */
 
 template <int G>
-constexpr size_t k4_smem_bytes() { return static_cast<size_t>(kDecThreads / G) * kDecRing; }
-
-/* One compressed stream seen as aligned big-endian 32-bit words. */
-struct DecInput {
-    const uint32_t *wbase;
-    uint32_t        nwords;
-    uint32_t        tail;     /* valid bytes in the last word, 0 = all four */
-    __device__ __forceinline__ uint32_t fetch(uint32_t w) const
-    {
-        if (w >= nwords) return 0u;
-        uint32_t v = bswap32(__ldg(wbase + w));
-        if (w == nwords - 1u && tail) v &= 0xFFFFFFFFu << (8u * (4u - tail));
-        return v;                                       /* bits past the end read as zero */
-    }
-};
+constexpr size_t k4_smem_bytes() { return static_cast<size_t>(kDecThreads / G) * kDecStreamSmem; }
 
 template <int G>
 __global__ void __launch_bounds__(kDecThreads)
@@ -68,18 +60,44 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     const uint32_t lane = lane_id();
     const uint32_t gl = lane % G;
     const uint32_t gshift = lane - gl;                  /* first lane of my group            */
-    uint8_t *ring = smem + static_cast<size_t>(threadIdx.x / G) * kDecRing;
+    /* shared memory is addressed by offset from the block's base (cheap LDS/STS forms) */
+    const uint32_t ring0 = (threadIdx.x / G) * kDecStreamSmem;
+    uint32_t      *words = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t in0 = (ring0 + kDecRing) / 4;        /* word index of my input buffer     */
     constexpr int      kPass = (static_cast<int>(kMaxExtLen) + G - 1) / G;
-    constexpr uint32_t kMaxLit = G < 7 ? G : 7;         /* literals per step: 9 * 7 <= 64 bits */
+    constexpr uint32_t kMaxLit = G < 7 ? G : 7;         /* literals per run: 9 * 7 <= 64 bits */
     constexpr uint32_t kGroupBits = (G == 32) ? 0xFFFFFFFFu : ((1u << (G & 31)) - 1u);
+    constexpr uint32_t kFillPerLane = 32 / G;           /* one refill = 32 words per stream   */
 
     /* per-stream state; identical in all lanes of a group */
     bool     active = false, exhausted = false, ext = false, vec_ok = false;
     uint32_t sid = 0, cap = 0, pos = 0, flushed = 0, off = 1;
-    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, wbase = 0; /* stream words [wbase, wbase+4)     */
-    uint64_t cur = 0, end = 0;                          /* bit cursor / end, from word 0      */
+    uint32_t cur = 0, end = 0;                          /* bit cursor / end, from word 0      */
+    uint32_t fill_hi = 0, nwords = 0, tail = 0;         /* words staged so far; stream extent */
+    const uint32_t *wbase = nullptr;
     uint8_t *dst = nullptr;
-    DecInput src{nullptr, 0, 0};
+
+    /* big-endian word w of the stream, zero past the end */
+    auto fetch = [&](uint32_t w) -> uint32_t {
+        if (w >= nwords) return 0u;
+        uint32_t v = bswap32(__ldg(wbase + w));
+        if (w == nwords - 1u && tail) v &= 0xFFFFFFFFu << (8u * (4u - tail));
+        return v;
+    };
+    /* stage words [fill_hi, fill_hi + 32) of my stream (whole group) */
+    auto refill = [&]() {
+#pragma unroll
+        for (uint32_t t = 0; t < kFillPerLane; t++) {
+            const uint32_t w = fill_hi + gl * kFillPerLane + t;
+            words[in0 + (w & (kDecInWords - 1u))] = fetch(w);
+        }
+        fill_hi += 32u;
+    };
+    /* 32 bits of the stream starting at bit position p */
+    auto bits32 = [&](uint32_t p) -> uint32_t {
+        const uint32_t w = p >> 5;
+        return __funnelshift_l(words[in0 + ((w + 1u) & (kDecInWords - 1u))], words[in0 + (w & (kDecInWords - 1u))], p & 31u);
+    };
 
     for (;;) {
         /* ---- idle groups fetch the next stream ---- */
@@ -94,19 +112,20 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 } else {
                     sid = s;
                     const uint8_t  *p = in + in_off[sid];
-                    const uint32_t  nin = in_len[sid];
+                    const uint32_t  nin = umin32(in_len[sid], 0x1FFFFF00u);   /* 32-bit bit positions */
                     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
                     const uint32_t  lead = static_cast<uint32_t>(a & 3u);
-                    src.wbase = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
-                    src.nwords = (lead + nin + 3u) >> 2;
-                    src.tail = (lead + nin) & 3u;
+                    wbase = reinterpret_cast<const uint32_t *>(a & ~static_cast<uintptr_t>(3));
+                    nwords = (lead + nin + 3u) >> 2;
+                    tail = (lead + nin) & 3u;
                     dst = out + out_off[sid];
                     cap = out_cap[sid];
                     vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
                     cur = 8u * lead;                    /* bytes before the stream in word 0 */
-                    end = cur + static_cast<uint64_t>(nin) * 8u;
-                    wbase = 0;
-                    w0 = src.fetch(0); w1 = src.fetch(1); w2 = src.fetch(2); w3 = src.fetch(3);
+                    end = cur + nin * 8u;
+                    fill_hi = 0;
+                    refill();
+                    refill();
                     pos = 0;
                     flushed = 0;
                     off = 1;
@@ -114,120 +133,118 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     active = true;
                 }
             }
+            __syncwarp();
         }
         if (__all_sync(LZS_FULL_MASK, !active)) break;
 
-        /* ---- 96 bits of the stream starting at the cursor ---- */
+        /* ---- keep at least 16 words staged ahead of the cursor ---- */
         {
-            const uint32_t wi = static_cast<uint32_t>(cur >> 5);
-            while (active && wbase < wi) {
-                w0 = w1; w1 = w2; w2 = w3;
-                w3 = src.fetch(wbase + 4u);
-                wbase++;
+            const bool low = active && fill_hi < (cur >> 5) + 16u;
+            if (__any_sync(LZS_FULL_MASK, low)) {
+                if (low) refill();
+                __syncwarp();
             }
         }
-        const uint32_t sh = static_cast<uint32_t>(cur) & 31u;
-        const uint32_t b0 = __funnelshift_l(w1, w0, sh);
-        const uint32_t b1 = __funnelshift_l(w2, w1, sh);
-        const uint32_t b2 = __funnelshift_l(w3, w2, sh);
-        const uint64_t left = end - cur;
-        uint32_t       avail = left > 0xFFFFu ? 0xFFFFu : static_cast<uint32_t>(left);
 
-        /* ---- phase A: a run of literals, one per lane (token gl starts at bit 9*gl) ---- */
-        uint32_t nlit = 0;
-        {
-            const uint32_t at = 9u * gl;                /* < 64 for gl < 7                    */
-            const uint64_t b01 = (static_cast<uint64_t>(b0) << 32) | b1;
-            const uint32_t field = static_cast<uint32_t>((b01 << (at & 63u)) >> 55);   /* 9 bits */
-            const bool     is_lit = active && !ext && gl < kMaxLit && (field >> 8) == 0u &&
-                                avail >= at + 9u && pos + gl < cap;
-            const uint32_t mine = (__ballot_sync(LZS_FULL_MASK, is_lit) >> gshift) & kGroupBits;
-            nlit = static_cast<uint32_t>(__ffs(static_cast<int>(~mine))) - 1u;          /* leading literals */
-            if (gl < nlit) ring[(pos + gl) & (kDecRing - 1u)] = static_cast<uint8_t>(field);
-        }
-        pos += nlit;
-        avail -= 9u * nlit;
-        uint32_t used = 9u * nlit;                      /* bits consumed this step            */
-        __syncwarp();
-
-        /* ---- phase B: at most one match / continuation token ---- */
-        bool     done = false;
-        uint32_t L = 0;
-        if (active) {
-            const uint32_t top = used < 32u ? __funnelshift_l(b1, b0, used) : __funnelshift_l(b2, b1, used - 32u);
-            if (avail == 0u || pos >= cap) {
-                done = true;
-            } else if (ext) {                           /* 4-bit continuation */
-                if (avail < 4u) {
-                    done = true;
-                } else {
-                    used += 4u;
-                    L = top >> 28;
-                    ext = (L == kMaxExtLen);
-                }
-            } else if ((top >> 31) == 0u) {             /* a literal phase A could not take   */
-                if (avail < 9u) done = true;            /* (8th in a row: next step)          */
-            } else {
-                const uint32_t is_short = (top >> 30) & 1u;
-                const uint32_t hdr = is_short ? 9u : 13u;
-                const uint32_t o = is_short ? ((top >> 23) & 0x7Fu) : ((top >> 19) & 0x7FFu);
-                const uint32_t code = (top << hdr) >> 28;
-                uint32_t       w, len;
-                if (code < 12u) { len = (code >> 2) + 2u; w = 2u; }
-                else            { len = code - 7u;        w = 4u; }
-                if (avail < hdr) {
-                    done = true;
-                } else if (o == 0u) {
-                    if (is_short) done = true;          /* end marker */
-                    else used += 13u;                   /* long offset 0: no length field */
-                } else if (avail < hdr + w) {
-                    done = true;
-                } else {
-                    used += hdr + w;
-                    L = len;
-                    off = o;
-                    ext = (len == kMaxShortLen);
-                }
-            }
-            L = umin32(L, cap - pos);
-            cur += used;
-        }
-
-        /* copy: read everything, then write (the ring is one byte larger than the window,
-         * so byte k+1 lands on the slot byte k reads at offset 2047) */
-        uint8_t v[kPass];
+        bool done = false;
 #pragma unroll
-        for (int t = 0; t < kPass; t++) {
-            const uint32_t k = gl + static_cast<uint32_t>(t) * G;
-            v[t] = 0;
-            if (k < L) {
-                uint32_t kk = k;
-                if (kk >= off) kk %= off;               /* overlap: periodic extension */
-                const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
-                if (s >= 0) v[t] = ring[static_cast<uint32_t>(s) & (kDecRing - 1u)];
+        for (int round = 0; round < kDecRounds; round++) {
+            const uint32_t avail = end - cur;
+            /* ---- a run of literals, one per lane (token gl starts 9*gl bits after the cursor) ---- */
+            uint32_t nlit;
+            {
+                const uint32_t at = 9u * gl;
+                const uint32_t field = bits32(cur + at) >> 23;                     /* 9 bits */
+                const bool     is_lit = active && !done && !ext && gl < kMaxLit && (field >> 8) == 0u &&
+                                    avail >= at + 9u && pos + gl < cap;
+                const uint32_t mine = (__ballot_sync(LZS_FULL_MASK, is_lit) >> gshift) & kGroupBits;
+                nlit = static_cast<uint32_t>(__ffs(static_cast<int>(~mine))) - 1u;  /* leading literals */
+                if (gl < nlit) smem[ring0 + ((pos + gl) & (kDecRing - 1u))] = static_cast<uint8_t>(field);
             }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < kPass; t++) {
-            const uint32_t k = gl + static_cast<uint32_t>(t) * G;
-            if (k < L) ring[(pos + k) & (kDecRing - 1u)] = v[t];
-        }
-        pos += L;
-        __syncwarp();
+            pos += nlit;
+            cur += 9u * nlit;
+            __syncwarp();
 
-        if (active && pos - flushed >= 16u * G) {
-            const uint32_t p = flushed + 16u * gl;
-            if (vec_ok) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(ring + (p & (kDecRing - 1u)));
-                *reinterpret_cast<uint4 *>(dst + p) = q;
-            } else {
-                for (uint32_t b = 0; b < 16u; b++) dst[p + b] = ring[(p + b) & (kDecRing - 1u)];
+            /* ---- at most one match / continuation token ---- */
+            uint32_t L = 0;
+            if (active && !done) {
+                const uint32_t left = end - cur;
+                const uint32_t top = bits32(cur);
+                uint32_t       used = 0;
+                if (left == 0u || pos >= cap) {
+                    done = true;
+                } else if (ext) {                       /* 4-bit continuation */
+                    if (left < 4u) {
+                        done = true;
+                    } else {
+                        used = 4u;
+                        L = top >> 28;
+                        ext = (L == kMaxExtLen);
+                    }
+                } else if ((top >> 31) == 0u) {         /* a literal the run could not take   */
+                    if (left < 9u) done = true;         /* (8th in a row: next round)         */
+                } else {
+                    const uint32_t is_short = (top >> 30) & 1u;
+                    const uint32_t hdr = is_short ? 9u : 13u;
+                    const uint32_t o = is_short ? ((top >> 23) & 0x7Fu) : ((top >> 19) & 0x7FFu);
+                    const uint32_t code = (top << hdr) >> 28;
+                    uint32_t       w, len;
+                    if (code < 12u) { len = (code >> 2) + 2u; w = 2u; }
+                    else            { len = code - 7u;        w = 4u; }
+                    if (left < hdr) {
+                        done = true;
+                    } else if (o == 0u) {
+                        if (is_short) done = true;      /* end marker */
+                        else used = 13u;                /* long offset 0: no length field */
+                    } else if (left < hdr + w) {
+                        done = true;
+                    } else {
+                        used = hdr + w;
+                        L = len;
+                        off = o;
+                        ext = (len == kMaxShortLen);
+                    }
+                }
+                L = umin32(L, cap - pos);
+                cur += used;
             }
-            flushed += 16u * G;
+
+            /* copy: read everything, then write (the ring is one byte larger than the window,
+             * so byte k+1 lands on the slot byte k reads at offset 2047) */
+            uint8_t v[kPass];
+#pragma unroll
+            for (int t = 0; t < kPass; t++) {
+                const uint32_t k = gl + static_cast<uint32_t>(t) * G;
+                v[t] = 0;
+                if (k < L) {
+                    uint32_t kk = k;
+                    if (kk >= off) kk %= off;           /* overlap: periodic extension */
+                    const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
+                    if (s >= 0) v[t] = smem[ring0 + (static_cast<uint32_t>(s) & (kDecRing - 1u))];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < kPass; t++) {
+                const uint32_t k = gl + static_cast<uint32_t>(t) * G;
+                if (k < L) smem[ring0 + ((pos + k) & (kDecRing - 1u))] = v[t];
+            }
+            pos += L;
+            __syncwarp();
+
+            if (active && pos - flushed >= 16u * G) {
+                const uint32_t p = flushed + 16u * gl;
+                if (vec_ok) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(smem + ring0 + (p & (kDecRing - 1u)));
+                    *reinterpret_cast<uint4 *>(dst + p) = q;
+                } else {
+                    for (uint32_t b = 0; b < 16u; b++) dst[p + b] = smem[ring0 + ((p + b) & (kDecRing - 1u))];
+                }
+                flushed += 16u * G;
+            }
         }
         if (active && done) {
-            for (uint32_t k = flushed + gl; k < pos; k += G) dst[k] = ring[k & (kDecRing - 1u)];
+            for (uint32_t k = flushed + gl; k < pos; k += G) dst[k] = smem[ring0 + (k & (kDecRing - 1u))];
             if (gl == 0) out_len[sid] = pos;
             active = false;
         }
