@@ -44,7 +44,15 @@ constexpr int      kDecThreads = 128;
 constexpr uint32_t kDecRing = 2048;                 /* history bytes per stream             */
 constexpr uint32_t kDecInWords = 64;                /* staged input words per stream        */
 constexpr uint32_t kDecStreamSmem = kDecRing + 4 * kDecInWords;
-constexpr int      kDecRounds = 3;                  /* (literal run + one token) per step   */
+#ifndef LZS_K4_ROUNDS
+#define LZS_K4_ROUNDS 4
+#endif
+constexpr int      kDecRounds = LZS_K4_ROUNDS;      /* (literal run + one token) per step   */
+constexpr uint32_t kDecAhead = 24;                  /* words kept staged ahead of the cursor */
+static_assert(kDecRounds * 80 + 64 <= 32 * static_cast<int>(kDecAhead), "a step may not outrun the staged input");
+
+template <bool B>
+struct CarefulTag { static constexpr bool value = B; };
 
 template <int G>
 constexpr size_t k4_smem_bytes() { return static_cast<size_t>(kDecThreads / G) * kDecStreamSmem; }
@@ -137,26 +145,30 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
         }
         if (__all_sync(LZS_FULL_MASK, !active)) break;
 
-        /* ---- keep at least 16 words staged ahead of the cursor ---- */
+        /* ---- keep kDecAhead words staged ahead of the cursor ---- */
         {
-            const bool low = active && fill_hi < (cur >> 5) + 16u;
+            const bool low = active && fill_hi < (cur >> 5) + kDecAhead;
             if (__any_sync(LZS_FULL_MASK, low)) {
                 if (low) refill();
                 __syncwarp();
             }
         }
 
-        bool done = false;
-#pragma unroll
-        for (int round = 0; round < kDecRounds; round++) {
-            const uint32_t avail = end - cur;
+        /* Far from the end of the input and of the output capacity nothing can run out
+         * within one step, so the bound checks of the reference's loop are only compiled
+         * into the "careful" variant used for the last steps of a stream. */
+        bool       done = false;
+        const bool near_end = active && (end - cur < 96u * static_cast<uint32_t>(kDecRounds) + 64u ||
+                                         cap - pos < 24u * static_cast<uint32_t>(kDecRounds) + 8u);
+        auto one_round = [&](auto careful_tag) {
+            constexpr bool kCareful = decltype(careful_tag)::value;
             /* ---- a run of literals, one per lane (token gl starts 9*gl bits after the cursor) ---- */
             uint32_t nlit;
             {
                 const uint32_t at = 9u * gl;
                 const uint32_t field = bits32(cur + at) >> 23;                     /* 9 bits */
-                const bool     is_lit = active && !done && !ext && gl < kMaxLit && (field >> 8) == 0u &&
-                                    avail >= at + 9u && pos + gl < cap;
+                bool           is_lit = active && !done && !ext && gl < kMaxLit && (field >> 8) == 0u;
+                if (kCareful) is_lit = is_lit && (end - cur >= at + 9u) && (pos + gl < cap);
                 const uint32_t mine = (__ballot_sync(LZS_FULL_MASK, is_lit) >> gshift) & kGroupBits;
                 nlit = static_cast<uint32_t>(__ffs(static_cast<int>(~mine))) - 1u;  /* leading literals */
                 if (gl < nlit) smem[ring0 + ((pos + gl) & (kDecRing - 1u))] = static_cast<uint8_t>(field);
@@ -168,10 +180,10 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             /* ---- at most one match / continuation token ---- */
             uint32_t L = 0;
             if (active && !done) {
-                const uint32_t left = end - cur;
                 const uint32_t top = bits32(cur);
+                const uint32_t left = kCareful ? end - cur : 0xFFFFu;
                 uint32_t       used = 0;
-                if (left == 0u || pos >= cap) {
+                if (kCareful && (left == 0u || pos >= cap)) {
                     done = true;
                 } else if (ext) {                       /* 4-bit continuation */
                     if (left < 4u) {
@@ -205,7 +217,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         ext = (len == kMaxShortLen);
                     }
                 }
-                L = umin32(L, cap - pos);
+                if (kCareful) L = umin32(L, cap - pos);
                 cur += used;
             }
 
@@ -231,17 +243,25 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             }
             pos += L;
             __syncwarp();
+        };
+        if (__any_sync(LZS_FULL_MASK, near_end)) {
+#pragma unroll
+            for (int round = 0; round < kDecRounds; round++) one_round(CarefulTag<true>{});
+        } else {
+#pragma unroll
+            for (int round = 0; round < kDecRounds; round++) one_round(CarefulTag<false>{});
+        }
 
-            if (active && pos - flushed >= 16u * G) {
-                const uint32_t p = flushed + 16u * gl;
-                if (vec_ok) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(smem + ring0 + (p & (kDecRing - 1u)));
-                    *reinterpret_cast<uint4 *>(dst + p) = q;
-                } else {
-                    for (uint32_t b = 0; b < 16u; b++) dst[p + b] = smem[ring0 + ((p + b) & (kDecRing - 1u))];
-                }
-                flushed += 16u * G;
+        /* flush once per step (a step adds at most kDecRounds * 22 bytes, far less than the ring) */
+        while (active && pos - flushed >= 16u * G) {
+            const uint32_t p = flushed + 16u * gl;
+            if (vec_ok) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(smem + ring0 + (p & (kDecRing - 1u)));
+                *reinterpret_cast<uint4 *>(dst + p) = q;
+            } else {
+                for (uint32_t b = 0; b < 16u; b++) dst[p + b] = smem[ring0 + ((p + b) & (kDecRing - 1u))];
             }
+            flushed += 16u * G;
         }
         if (active && done) {
             for (uint32_t k = flushed + gl; k < pos; k += G) dst[k] = smem[ring0 + (k & (kDecRing - 1u))];
