@@ -39,6 +39,7 @@ static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) {
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
