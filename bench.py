@@ -297,7 +297,7 @@ def run_gpu_arm(args):
         if e2e:
             line["e2e"] = {"value": job_bytes / (t_e2e * 1e-3) / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "steps": e2e["steps"], "api": "lzs_b200_compress_batch_host + lzs_b200_decompress_batch_host"}
+                           "steps": e2e["steps"], "api": "lzs_b200_compress_packed_host + lzs_b200_decompress_batch_host"}
         if gather:
             line["gather"] = gather
         if world == 1 and not args.no_cpu:
@@ -328,11 +328,15 @@ def run_e2e(B, db, total, n_chunks, steps, barrier):
     def p(t):
         return ctypes.cast(t.data_ptr(), u8)
 
+    c_offp = np.zeros(n_chunks, dtype=np.uint64)
+    used = np.zeros(1, dtype=np.uint64)
+
     def step():
-        B.check(L.lzs_b200_compress_batch_host(p(raw), B._p(in_off, u64), B._p(in_len, u32), total, p(comp),
-                                               B._p(c_off, u64), B._p(c_cap, u32), B._p(c_len, u32),
-                                               n_chunks * stride, n_chunks))
-        B.check(L.lzs_b200_decompress_batch_host(p(comp), B._p(c_off, u64), B._p(c_len, u32), n_chunks * stride,
+        # compress to packed streams (only compressed bytes cross PCIe), then decompress from them
+        B.check(L.lzs_b200_compress_packed_host(p(raw), B._p(in_off, u64), B._p(in_len, u32), total, p(comp),
+                                                n_chunks * stride, B._p(c_offp, u64), B._p(c_len, u32), n_chunks,
+                                                B._p(used, u64)))
+        B.check(L.lzs_b200_decompress_batch_host(p(comp), B._p(c_offp, u64), B._p(c_len, u32), int(used[0]),
                                                  p(dec), B._p(in_off, u64), B._p(in_len, u32), B._p(d_len, u32),
                                                  total, n_chunks))
 
@@ -344,10 +348,10 @@ def run_e2e(B, db, total, n_chunks, steps, barrier):
     barrier()
     ms = (time.perf_counter() - t0) * 1e3 / steps
     assert torch.equal(dec[:total], raw[:total]), "e2e round trip mismatch"
-    hi = int((c_off + c_len.astype(np.uint64)).max())
+    packed = int(used[0])
     arrays = n_chunks * 24
-    h2d = total + arrays + n_chunks * stride + arrays      # compress input + decompress input span
-    d2h = hi + 4 * n_chunks + total + 4 * n_chunks
+    h2d = total + arrays + 8 * n_chunks + packed + arrays  # compress input (+ tables), decompress input = packed streams
+    d2h = packed + 4 * n_chunks + total + 4 * n_chunks
     return {"ms": ms, "h2d": int(h2d), "d2h": int(d2h), "steps": steps}
 
 

@@ -89,6 +89,16 @@ int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, co
                                    const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
                                    uint32_t n_streams);
 
+/* Packed variant of lzs_b200_compress_batch_host for streams given in increasing order (chunks of
+ * a file, a packet table): the streams are written back to back, each starting at a multiple of
+ * 16, and out_off[s] / out_len[s] are OUTPUTS.  Only compressed bytes travel back over PCIe, and
+ * the concatenation (minus the padding) is what the reference's lzs-decompress reads marker by
+ * marker.  out_capacity: LZS_COMPRESSED_MAX of every stream rounded up to 16 always suffices.
+ * *out_used (may be NULL) receives the bytes of `out` covered. */
+int lzs_b200_compress_packed_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                  uint64_t in_span, uint8_t *out, uint64_t out_capacity, uint64_t *out_off,
+                                  uint32_t *out_len, uint32_t n_streams, uint64_t *out_used);
+
 /* ------------------------------------------------------------------------------
  * Batch form of the incremental calls of lzs.h (reference lzs.h:222, :232): advance
  * n independent caller-owned streams by ONE lzs_compress_incremental /

@@ -109,6 +109,19 @@ __global__ void corpus_fill_kernel(uint8_t *dst, uint64_t stride, uint32_t strea
     if (s < n) lzs_corpus_fill(dst + s * stride, stream_len, seed, first_index + s, kind);
 }
 
+/* Copy n streams from their slots to packed positions; both offsets are multiples of 16. */
+__global__ void gather_streams_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                                      const uint32_t *__restrict__ len, uint8_t *__restrict__ dst,
+                                      const uint64_t *__restrict__ dst_off, uint32_t n)
+{
+    const uint32_t s = blockIdx.x;
+    if (s >= n) return;
+    const uint4   *from = reinterpret_cast<const uint4 *>(src + src_off[s]);
+    uint4         *to = reinterpret_cast<uint4 *>(dst + dst_off[s]);
+    const uint32_t vecs = (len[s] + 15u) >> 4;
+    for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) to[i] = from[i];
+}
+
 }  // namespace
 
 extern "C" {
@@ -284,8 +297,8 @@ struct HostPath {
     cudaStream_t stream = nullptr;          /* copies of small arrays, simple path        */
     cudaStream_t work[8] = {};              /* slice k: upload + kernels on work[k % 8]   */
     cudaStream_t down = nullptr;            /* downloads of finished slices               */
-    void        *buf[9] = {};
-    size_t       cap[9] = {};
+    void        *buf[11] = {};
+    size_t       cap[11] = {};
     uint32_t    *pinned_len = nullptr;      /* pinned staging for per-stream result lengths */
     size_t       pinned_cap = 0;
 
@@ -338,7 +351,7 @@ int host_path(HostPath **out)
     return LZS_B200_OK;
 }
 
-enum { S_IN, S_OUT, S_INOFF, S_INLEN, S_OUTOFF, S_OUTCAP, S_OUTLEN, S_SCRATCH, S_COUNTERS };
+enum { S_IN, S_OUT, S_INOFF, S_INLEN, S_OUTOFF, S_OUTCAP, S_OUTLEN, S_SCRATCH, S_COUNTERS, S_PACKED, S_PACKOFF };
 
 /* Uncompressed bytes per pipeline slice: a quarter of the batch, between 32 and 256 MiB
  * (measured on B200, 1 GiB batch: 256 MiB slices give 86 ms compress / 43 ms decompress
@@ -502,6 +515,129 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     return LZS_B200_OK;
 }
 
+/* Compress n ordered streams and return them PACKED: out_off[s] (written here, multiples of
+ * 16) and out_len[s]; the bytes between streams are padding.  Same sliced pipeline as
+ * run_host_batch, plus a gather kernel per slice, so only compressed bytes cross PCIe. */
+int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint64_t in_span,
+                        uint8_t *out, uint64_t out_capacity, uint64_t *out_off, uint32_t *out_len, uint32_t n,
+                        uint64_t *out_used)
+{
+    if (out_used) *out_used = 0;
+    if (n == 0) return LZS_B200_OK;
+    if (!in_off || !in_len || !out_off || !out_len || (!in && in_span) || !out)
+        return fail(LZS_B200_EINVAL, "null pointer");
+    for (uint32_t s2 = 1; s2 < n; s2++)
+        if (in_off[s2] < in_off[s2 - 1] + in_len[s2 - 1])
+            return fail(LZS_B200_EINVAL, "packed compression needs streams in increasing, non-overlapping order");
+    if (lzs_b200_device_count() <= 0) return fail(LZS_B200_ENODEVICE, "no CUDA device: the LZS codec has no CPU path");
+    HostPath *hp = nullptr;
+    int       rc = host_path(&hp);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(hp->mu);
+    HostPath    &p = *hp;
+    cudaStream_t st = p.stream;
+
+    /* internal slots: worst-case size of every stream, 16-byte aligned */
+    std::vector<uint64_t> slot_off(n);
+    std::vector<uint32_t> slot_cap(n);
+    uint64_t              slots = 0;
+    for (uint32_t s2 = 0; s2 < n; s2++) {
+        slot_off[s2] = slots;
+        slot_cap[s2] = static_cast<uint32_t>(align_up(LZS_COMPRESSED_MAX(static_cast<size_t>(in_len[s2])), 16));
+        slots += slot_cap[s2];
+    }
+    std::vector<uint32_t> first;
+    const uint64_t        per_slice = slice_bytes(in_span);
+    uint64_t              acc = per_slice;
+    for (uint32_t s2 = 0; s2 < n; s2++) {
+        if (acc >= per_slice) { first.push_back(s2); acc = 0; }
+        acc += in_len[s2];
+    }
+    const uint32_t nslice = static_cast<uint32_t>(first.size());
+    first.push_back(n);
+
+    if ((rc = p.reserve(S_IN, in_span + 64))) return rc;
+    if ((rc = p.reserve(S_OUT, slots + 64))) return rc;
+    if ((rc = p.reserve(S_PACKED, out_capacity + 64))) return rc;
+    if ((rc = p.reserve(S_INOFF, n * sizeof(uint64_t)))) return rc;
+    if ((rc = p.reserve(S_INLEN, n * sizeof(uint32_t)))) return rc;
+    if ((rc = p.reserve(S_OUTOFF, n * sizeof(uint64_t)))) return rc;
+    if ((rc = p.reserve(S_OUTCAP, n * sizeof(uint32_t)))) return rc;
+    if ((rc = p.reserve(S_OUTLEN, n * sizeof(uint32_t)))) return rc;
+    if ((rc = p.reserve(S_PACKOFF, n * sizeof(uint64_t)))) return rc;
+    if ((rc = p.reserve(S_SCRATCH, lzs_b200_compress_scratch_bytes(in_span)))) return rc;
+    if ((rc = p.reserve(S_COUNTERS, static_cast<size_t>(nslice) * 512))) return rc;
+    if ((rc = p.reserve_pinned(n))) return rc;
+    uint8_t  *d_in = static_cast<uint8_t *>(p.buf[S_IN]);
+    uint8_t  *d_slots = static_cast<uint8_t *>(p.buf[S_OUT]);
+    uint8_t  *d_packed = static_cast<uint8_t *>(p.buf[S_PACKED]);
+    uint8_t  *d_cnt = static_cast<uint8_t *>(p.buf[S_COUNTERS]);
+    uint64_t *d_inoff = static_cast<uint64_t *>(p.buf[S_INOFF]);
+    uint32_t *d_inlen = static_cast<uint32_t *>(p.buf[S_INLEN]);
+    uint64_t *d_slotoff = static_cast<uint64_t *>(p.buf[S_OUTOFF]);
+    uint32_t *d_slotcap = static_cast<uint32_t *>(p.buf[S_OUTCAP]);
+    uint32_t *d_outlen = static_cast<uint32_t *>(p.buf[S_OUTLEN]);
+    uint64_t *d_packoff = static_cast<uint64_t *>(p.buf[S_PACKOFF]);
+    uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(p.buf[S_SCRATCH]) + kCounterBytes);
+
+    CUDA_TRY(cudaMemcpyAsync(d_inoff, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_inlen, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_slotoff, slot_off.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_slotcap, slot_cap.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    std::vector<cudaEvent_t> ev(nslice + 1);
+    for (auto &e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev[nslice], st));
+    for (auto &w : p.work) CUDA_TRY(cudaStreamWaitEvent(w, ev[nslice], 0));
+    for (uint32_t k = 0; k < nslice && !rc; k++) {
+        const uint32_t a = first[k], b = first[k + 1], cnt = b - a;
+        cudaStream_t   ws = p.work[k % 8u];
+        const uint64_t lo = in_off[a], hi = in_off[b - 1] + in_len[b - 1];
+        if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, ws));
+        rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
+                                         reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
+        if (!rc)
+            rc = lzs_b200_parse_pack_batch_device(d_in, d_inoff + a, d_inlen + a, matches, d_slots, d_slotoff + a,
+                                                  d_slotcap + a, d_outlen + a, cnt, ws);
+        if (rc) break;
+        CUDA_TRY(cudaMemcpyAsync(p.pinned_len + a, d_outlen + a, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws));
+        CUDA_TRY(cudaEventRecord(ev[k], ws));
+    }
+    uint64_t cursor = 0;
+    for (uint32_t k = 0; k < nslice && !rc; k++) {
+        const uint32_t a = first[k], b = first[k + 1], cnt = b - a;
+        CUDA_TRY(cudaEventSynchronize(ev[k]));
+        memcpy(out_len + a, p.pinned_len + a, cnt * sizeof(uint32_t));
+        const uint64_t begin = cursor;
+        for (uint32_t s2 = a; s2 < b; s2++) {
+            out_off[s2] = cursor;
+            cursor += align_up(out_len[s2], 16);
+        }
+        if (cursor > out_capacity) {
+            rc = fail(LZS_B200_EINVAL, "packed output needs more than the %llu bytes offered",
+                      static_cast<unsigned long long>(out_capacity));
+            break;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_packoff + a, out_off + a, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, p.down));
+        gather_streams_kernel<<<cnt, 128, 0, p.down>>>(d_slots, d_slotoff + a, d_outlen + a, d_packed, d_packoff + a, cnt);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (cursor > begin)
+            CUDA_TRY(cudaMemcpyAsync(out + begin, d_packed + begin, cursor - begin, cudaMemcpyDeviceToHost, p.down));
+    }
+    cudaError_t e1 = cudaSuccess;
+    for (auto &w : p.work) {
+        cudaError_t e = cudaStreamSynchronize(w);
+        if (e != cudaSuccess) e1 = e;
+    }
+    cudaError_t e3 = cudaStreamSynchronize(p.down);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    CUDA_TRY(e1);
+    CUDA_TRY(e3);
+    if (out_used) *out_used = cursor;
+    return LZS_B200_OK;
+}
+
 /* single stream through the host path; loud on failure, 0 bytes as the reference's
  * only "error" value */
 size_t single_call(bool decompress, uint8_t *out, size_t out_cap, const uint8_t *in, size_t in_len)
@@ -538,6 +674,13 @@ int lzs_b200_compress_batch_host(const uint8_t *in, const uint64_t *in_off, cons
                                  uint32_t n_streams)
 {
     return run_host_batch(false, in, in_off, in_len, in_span, out, out_off, out_cap, out_len, out_span, n_streams);
+}
+
+int lzs_b200_compress_packed_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                  uint64_t in_span, uint8_t *out, uint64_t out_capacity, uint64_t *out_off,
+                                  uint32_t *out_len, uint32_t n_streams, uint64_t *out_used)
+{
+    return run_compress_packed(in, in_off, in_len, in_span, out, out_capacity, out_off, out_len, n_streams, out_used);
 }
 
 int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,

@@ -75,6 +75,8 @@ def lib():
     host = [u8p, u64p, u32p, ctypes.c_uint64, u8p, u64p, u32p, u32p, ctypes.c_uint64, ctypes.c_uint32]
     L.lzs_b200_compress_batch_host.argtypes = host
     L.lzs_b200_decompress_batch_host.argtypes = host
+    L.lzs_b200_compress_packed_host.argtypes = [u8p, u64p, u32p, ctypes.c_uint64, u8p, ctypes.c_uint64, u64p, u32p,
+                                                ctypes.c_uint32, u64p]
     L.lzs_b200_corpus_fill_device.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
                                               ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp]
     L.lzs_b200_set_decode_lanes.argtypes = [ctypes.c_int]
@@ -164,6 +166,25 @@ def compress_streams(streams, caps=None):
     out_off, out_cap, out_span = layout(caps)
     dst, out_len = _host_batch(lib().lzs_b200_compress_batch_host, src, in_off, in_len, out_off, out_cap, out_span)
     return [dst[int(o):int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+
+
+def compress_streams_packed(streams):
+    """Like compress_streams, through lzs_b200_compress_packed_host: returns (packed buffer,
+    offsets, lengths); stream s is packed[off[s] : off[s] + len[s]]."""
+    streams = [bytes(s) for s in streams]
+    in_off, in_len, in_span = layout([len(s) for s in streams])
+    src = np.zeros(in_span + 64, dtype=np.uint8)
+    for o, s in zip(in_off, streams):
+        src[int(o):int(o) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    n = len(streams)
+    cap = sum(aligned_stride(compressed_max(len(s))) for s in streams)
+    dst = np.zeros(cap + 64, dtype=np.uint8)
+    out_off = np.zeros(max(n, 1), dtype=np.uint64)
+    out_len = np.zeros(max(n, 1), dtype=np.uint32)
+    used = np.zeros(1, dtype=np.uint64)
+    check(lib().lzs_b200_compress_packed_host(_p(src), _p(in_off, u64p), _p(in_len, u32p), in_span, _p(dst), cap,
+                                              _p(out_off, u64p), _p(out_len, u32p), n, _p(used, u64p)))
+    return dst[:int(used[0])], out_off[:n], out_len[:n]
 
 
 def decompress_streams(streams, caps):

@@ -193,3 +193,25 @@ def test_full_size_packets_roundtrip(B):
         raw = db.raw[s * plen:(s + 1) * plen].cpu().numpy().tobytes()
         got = db.comp[s * db.comp_stride:s * db.comp_stride + int(lens[s])].cpu().numpy().tobytes()
         assert got == ref.compress(raw), s
+
+
+def test_packed_host_compression(B):
+    """lzs_b200_compress_packed_host: same streams as the slot layout, back to back at multiples
+    of 16, and the packed buffer feeds lzs_b200_decompress_batch_host directly."""
+    o = helpers.oracle()
+    rng = np.random.default_rng(8)
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, int(rng.integers(0, 9000)), first_index=i).tobytes()
+            for i in range(300)]
+    packed, off, ln = B.compress_streams_packed(data)
+    want = [o.compress(d) for d in data]
+    assert [packed[int(a):int(a) + int(l)].tobytes() for a, l in zip(off, ln)] == want
+    assert all(int(a) % 16 == 0 for a in off) and int(off[-1]) + int(ln[-1]) <= len(packed)
+    assert all(int(off[i + 1]) - int(off[i]) < int(ln[i]) + 16 for i in range(len(off) - 1))      # really packed
+    dst = np.zeros(sum(len(d) for d in data) + 64, dtype=np.uint8)
+    raw_off, raw_len, raw_span = B.layout([len(d) for d in data], align=1)
+    d_len = np.zeros(len(data), dtype=np.uint32)
+    B.check(B.lib().lzs_b200_decompress_batch_host(B._p(packed), B._p(off, B.u64p), B._p(ln, B.u32p), len(packed),
+                                                   B._p(dst), B._p(raw_off, B.u64p), B._p(raw_len, B.u32p),
+                                                   B._p(d_len, B.u32p), raw_span, len(data)))
+    assert (d_len == raw_len).all()
+    assert dst[:raw_span].tobytes() == b"".join(data)
