@@ -58,7 +58,8 @@ int lzs_b200_compress_batch_device(const uint8_t *in, const uint64_t *in_off, co
                                    const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams,
                                    void *scratch, size_t scratch_bytes, void *stream);
 
-/* batch form of lzs_decompress (reference lzs.h:229) */
+/* batch form of lzs_decompress (reference lzs.h:229); a compressed stream may be at most
+ * 512 MiB - 256 B long (the decoder keeps 32-bit bit positions) */
 int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                                      uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
                                      uint32_t *out_len, uint32_t n_streams, void *scratch,
