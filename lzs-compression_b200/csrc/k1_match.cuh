@@ -73,7 +73,10 @@ constexpr uint32_t kK1WRing = 8192;
 constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 992 = 31 batches  */
 constexpr uint32_t kK1StreamGap = 16;       /* virtual positions between streams   */
 constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the run-table warp */
-constexpr int      kK1QueryWarps = 16;
+#ifndef LZS_K1_QW
+#define LZS_K1_QW 16
+#endif
+constexpr int      kK1QueryWarps = LZS_K1_QW;
 constexpr int      kK1Threads = 32 * (kK1BuildWarps + kK1QueryWarps);
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
@@ -235,6 +238,13 @@ __device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W,
  * whose chain ends without a verified candidate ends the search ("some candidate
  * reaches k" is monotone in k).  Every chain link carries the 5-bit tag of the entry
  * it belongs to, so a foreign entry costs one shared-memory load. */
+#if defined(LZS_SIMT_EMU) && defined(LZS_K1_STATS)
+extern "C" unsigned long long g_k1_stats[8];   /* queries, steps, foreign, verified-fail, levels, run skips, max steps */
+#define LZS_STAT(i, v) (g_k1_stats[i] += (v))
+#else
+#define LZS_STAT(i, v) ((void)0)
+#endif
+
 __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16_t *runs, const uint32_t *W,
                                              uint32_t v0, uint32_t i, uint32_t n)
 {
@@ -252,13 +262,16 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
     uint32_t tag = e >> 11;
     uint32_t d = e & kLinkDistMask;
     uint32_t tot = 0;
+    LZS_STAT(0, 1); LZS_STAT(4, 1);
     for (;;) {
         tot += d;
         if (d == 0 || tot > maxd) break;                     /* level k has no candidate: done */
+        LZS_STAT(1, 1);
         const uint32_t j = v - tot;
         e = lk[j & (kK1LinkRing - 1)];
         d = e & kLinkDistMask;
         if ((e >> 11) != tag) {                              /* foreign entry of this slot  */
+            LZS_STAT(2, 1);
             if (d == 1u) {
                 /* its predecessor is the adjacent position: if j sits inside a run of one
                  * byte value that covers k bytes from j, every run member before j has j's
@@ -267,6 +280,7 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
                 const uint32_t back = r & kRunBackMask;
                 if ((r >> 12) >= k && back != 0u) {
                     tot += back;
+                    LZS_STAT(5, 1);
                     d = lk[(j - back) & (kK1LinkRing - 1)] & kLinkDistMask;
                 }
             }
@@ -274,7 +288,8 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
         }
         const uint32_t l = umin32(lcp12(w0, w1, w2, W[j & (kK1WRing - 1)], W[(j + 4) & (kK1WRing - 1)],
                                         W[(j + 8) & (kK1WRing - 1)]), M);
-        if (l < k) continue;
+        if (l < k) { LZS_STAT(3, 1); continue; }
+        LZS_STAT(4, 1);
         best = l;                                            /* nearest candidate of length l */
         bd = tot;
         if (l >= M) break;
