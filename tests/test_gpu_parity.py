@@ -215,3 +215,45 @@ def test_packed_host_compression(B):
                                                    B._p(d_len, B.u32p), raw_span, len(data)))
     assert (d_len == raw_len).all()
     assert dst[:raw_span].tobytes() == b"".join(data)
+
+
+def test_structured_fuzz_against_cpu_codec(B):
+    """2000 structured random streams in one batch (alphabets of 2/3/20/256 symbols, copies planted
+    at distances around the window edge, runs, sizes 0..12000) -- bit-exact compress, and the
+    decoder on the compressed streams, on truncated streams and on bit-flipped streams."""
+    cpu = helpers.reference() or helpers.oracle()
+    rng = np.random.default_rng(4242)
+    data = []
+    for it in range(2000):
+        n = int(rng.integers(0, 12000)) if it % 10 else int(rng.integers(0, 40))
+        alpha = int(rng.choice([2, 3, 20, 256]))
+        buf = bytearray(rng.integers(0, alpha, n, dtype=np.uint8).tobytes())
+        for _ in range(int(rng.integers(0, 8))):
+            if n < 2200:
+                break
+            d = int(rng.choice([1, 2, 3, 7, 127, 128, 2040, 2046, 2047, 2048, 2060]))
+            p = int(rng.integers(d, n - 1))
+            ln = int(rng.integers(2, 300))
+            buf[p:p + ln] = buf[p - d:p - d + ln]
+        if it % 7 == 0 and n > 100:
+            p = int(rng.integers(0, n - 50))
+            buf[p:p + 40] = bytes([int(rng.integers(0, 256))]) * 40
+        data.append(bytes(buf[:n]))
+    want = [cpu.compress(d) for d in data]
+    got = B.compress_streams(data)
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, bad[:10]
+    assert B.decompress_streams(got, [len(d) for d in data]) == data
+    # damaged streams: truncate, flip a bit; capacity sometimes too small
+    damaged, caps = [], []
+    for i, w in enumerate(want[:600]):
+        s = bytearray(w)
+        if i % 3 == 0 and len(s) > 3:
+            s = s[:int(rng.integers(1, len(s)))]
+        elif i % 3 == 1 and len(s) > 0:
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+        damaged.append(bytes(s))
+        caps.append(int(rng.integers(0, 2 * len(data[i]) + 50)))
+    got = B.decompress_streams(damaged, caps)
+    for s, c, g in zip(damaged, caps, got):
+        assert g == cpu.decompress(s, c)
