@@ -85,7 +85,8 @@ constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 
 /* run table entry: (forward run length capped at 12) << 12 | distance back to the run start */
 constexpr uint32_t kRunBackMask = 0xFFFu;
 static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
-static_assert(kWindow + 3 * (kK1Tile + kK1StreamGap) + 16 < kK1WRing, "gram ring must hold one tile more than the links");
+constexpr uint32_t kK1Ahead = 40;           /* grams filled beyond the tile being built */
+static_assert(kWindow + 3 * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring must hold one tile more than the links");
 
 enum { kBarBuild = 1, kBarFull0 = 2, kBarFull1 = 3, kBarEmpty0 = 4, kBarEmpty1 = 5 };
 constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
@@ -342,11 +343,14 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
                 const uint32_t buf = g & 1u;
                 const uint32_t tile_n = umin32(kK1Tile, n - t0);
-                /* 4-byte grams of the new positions (+8 look-ahead for 12-byte compares).  Done
-                 * BEFORE waiting for the query group: the gram ring is large enough that these
-                 * slots are free, so the global-load latency hides in that wait. */
-                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + 8u;
-                const uint32_t p_hi = umin32(t0 + kK1Tile + 8u, n + 12u);
+                /* 4-byte grams of the new positions, kK1Ahead beyond the tile: 8 for the 12-byte
+                 * compares plus the 32 positions whose hashes the build warps prefetch in their
+                 * last batch (so a warp that is already filling the next tile never writes a gram
+                 * a slower warp still reads).  Done BEFORE waiting for the query group: the gram
+                 * ring is large enough that these slots are free, so the global-load latency
+                 * hides in that wait. */
+                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + kK1Ahead;
+                const uint32_t p_hi = umin32(t0 + kK1Tile + kK1Ahead, n + 12u);
                 for (uint32_t p = p_lo + tid; p < p_hi; p += kK1BuildThreads)
                     W[(v0 + p) & (kK1WRing - 1)] = (p < n) ? load4_unaligned(src + p, end) : 0u;
                 if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);

@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel, odd sizes,
+unaligned streams, truncated capacities, damaged streams, incremental calls."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lzs-compression_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import lzs_b200 as B
+import helpers
+o = helpers.oracle()
+rng = np.random.default_rng(1)
+data = list(helpers.edge_case_inputs().values())
+data += [helpers.corpus(helpers.CORPUS_MIXED, 1, int(rng.integers(1, 5000)), first_index=i).tobytes() for i in range(40)]
+data += [helpers.corpus(helpers.CORPUS_PACKET, 1, 1500, first_index=i).tobytes() for i in range(40)]
+comp = B.compress_streams(data)
+assert comp == [o.compress(d) for d in data]
+assert B.decompress_streams(comp, [len(d) for d in data]) == data
+caps = [max(0, len(c) - 3) for c in comp]
+assert B.compress_streams(data, caps=caps) == [c[:k] for c, k in zip(comp, caps)]
+dam = [c[:max(0, len(c) // 2)] for c in comp] + [bytes(rng.integers(0, 256, 100, dtype=np.uint8)) for _ in range(20)]
+got = B.decompress_streams(dam, [700] * len(dam))
+assert got == [o.decompress(s, 700) for s in dam]
+packed, off, ln = B.compress_streams_packed(data)
+assert [packed[int(a):int(a) + int(l)].tobytes() for a, l in zip(off, ln)] == comp
+for lanes in (4, 16, 32, 8):
+    B.check(B.lib().lzs_b200_set_decode_lanes(lanes))
+    assert B.decompress_streams(comp[:30], [len(d) for d in data[:30]]) == data[:30]
+assert B.lzs_compress(data[5]) == comp[5] and B.lzs_decompress(comp[5], len(data[5])) == data[5]
+import ctypes, inc_drivers as D
+ours = D.StructCodec(B.lib())
+out, _ = D.drive(ours, False, data[-1], 200, 100, 4000)
+assert out == comp[-1]
+back, _ = D.drive(ours, True, comp[-1], 50, 70, 1600)
+assert back == data[-1]
+print("sanitize workload ok")
