@@ -67,11 +67,15 @@ constexpr int      kK1Levels = 11;          /* k = 2 .. 12 */
 constexpr uint32_t kK1Slots = 4096;
 constexpr uint32_t kK1LinkRing = 4096;      /* >= 2047 + 2 * (tile + gap)          */
 constexpr uint32_t kK1WRing = 8192;
+constexpr uint32_t kK1WMirror = 64;         /* the first grams again behind the ring: index, +4, +8 need one wrap */
 #ifndef LZS_K1_TILE
-#define LZS_K1_TILE 992
+#define LZS_K1_TILE 960
 #endif
-constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 992 = 31 batches  */
-constexpr uint32_t kK1StreamGap = 16;       /* virtual positions between streams   */
+constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 960 = 30 batches  */
+/* Virtual positions between streams: 12 zero grams behind the last byte, then up to the next
+ * multiple of 32 (every stream starts on a batch boundary, so a batch never straddles a ring
+ * wrap and the positions a last batch inserts past the end of its stream belong to no stream). */
+constexpr uint32_t kK1StreamGap = 16 + 31;
 constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the run-table warp */
 #ifndef LZS_K1_QW
 #define LZS_K1_QW 16
@@ -81,11 +85,14 @@ constexpr int      kK1Threads = 32 * (kK1BuildWarps + kK1QueryWarps);
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
 constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 +
-                                static_cast<size_t>(kK1Levels + 1) * kK1LinkRing * 2 + kK1WRing * 4;
+                                static_cast<size_t>(kK1Levels + 1) * kK1LinkRing * 2 +
+                                (kK1WRing + kK1WMirror) * 4;
 /* run table entry: (forward run length capped at 12) << 12 | distance back to the run start */
 constexpr uint32_t kRunBackMask = 0xFFFu;
 static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
 constexpr uint32_t kK1Ahead = 40;           /* grams filled beyond the tile being built */
+constexpr int      kK1FillPerThread = static_cast<int>((kK1Tile + kK1BuildThreads - 1) / kK1BuildThreads);
+static_assert(kK1BuildThreads % 4 == 0, "one byte shift per thread for all its gram loads");
 static_assert(kWindow + 3 * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring must hold one tile more than the links");
 
 enum { kBarBuild = 1, kBarFull0 = 2, kBarFull1 = 3, kBarEmpty0 = 4, kBarEmpty1 = 5 };
@@ -101,33 +108,22 @@ __device__ __forceinline__ constexpr uint32_t low_bytes_mask(int bytes)
     return bytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * bytes)) - 1u);
 }
 
-/* Hash of the k-gram that starts the 12 bytes (w0, w1, w2): bits 31..20 are the table
+/* Hash of the K-gram that starts the 12 bytes (w0, w1, w2): bits 31..20 are the table
  * slot, bits 19..15 a 5-bit tag kept beside every chain link so that a query can
- * reject most foreign entries of its slot without touching their bytes. */
-__device__ __forceinline__ uint32_t gram_hash(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t m0,
-                                              uint32_t m1, uint32_t m2)
-{
-    uint32_t h = (w0 & m0) * 0x9E3779B1u;
-    h = (h ^ (w1 & m1)) * 0x85EBCA77u;
-    h = (h ^ (w2 & m2)) * 0xC2B2AE3Du;
-    h ^= h >> 15;
-    h *= 0x27D4EB2Fu;
-    return h;
-}
-__device__ __forceinline__ uint32_t gram_hash_k(uint32_t k, uint32_t w0, uint32_t w1, uint32_t w2)
-{
-    const uint32_t m0 = k >= 4u ? 0xFFFFFFFFu : ((1u << (8u * k)) - 1u);
-    const uint32_t m1 = k >= 8u ? 0xFFFFFFFFu : (k <= 4u ? 0u : ((1u << (8u * (k - 4u))) - 1u));
-    const uint32_t m2 = k >= 12u ? 0xFFFFFFFFu : (k <= 8u ? 0u : ((1u << (8u * (k - 8u))) - 1u));
-    return gram_hash(w0, w1, w2, m0, m1, m2);
-}
+ * reject most foreign entries of its slot without touching their bytes.  The three
+ * products are independent (one dependent multiply less than a chained hash). */
 template <int K>
 __device__ __forceinline__ uint32_t gram_hash_c(uint32_t w0, uint32_t w1, uint32_t w2)
 {
     constexpr uint32_t m0 = low_bytes_mask(K >= 4 ? 4 : K);
     constexpr uint32_t m1 = K <= 4 ? 0u : low_bytes_mask(K >= 8 ? 4 : K - 4);
     constexpr uint32_t m2 = K <= 8 ? 0u : low_bytes_mask(K >= 12 ? 4 : K - 8);
-    return gram_hash(w0, w1, w2, m0, m1, m2);
+    uint32_t h = (w0 & m0) * 0x9E3779B1u;
+    if (K > 4) h ^= (w1 & m1) * 0x85EBCA77u;
+    if (K > 8) h ^= (w2 & m2) * 0xC2B2AE3Du;
+    h ^= h >> 15;
+    h *= 0x27D4EB2Fu;
+    return h;
 }
 constexpr uint32_t kSlotShift = 20;          /* slot = h >> 20 (12 bits)                    */
 constexpr uint32_t kTagShift = 15;           /* tag  = (h >> 15) & 31                       */
@@ -144,58 +140,58 @@ __device__ __forceinline__ uint32_t lcp12(uint32_t a0, uint32_t a1, uint32_t a2,
     return 12u;
 }
 
+/* hash of the K-gram at gram-ring index x (x < kK1WRing; the mirror covers x + 8) */
 template <int K>
-__device__ __forceinline__ uint32_t k1_hash_at(const uint32_t *W, uint32_t v)
+__device__ __forceinline__ uint32_t k1_hash_at(const uint32_t *W, uint32_t x)
 {
-    return gram_hash_c<K>(W[v & (kK1WRing - 1)], W[(v + 4) & (kK1WRing - 1)], W[(v + 8) & (kK1WRing - 1)]);
+    return gram_hash_c<K>(W[x], K > 4 ? W[x + 4] : 0u, K > 8 ? W[x + 8] : 0u);
 }
 
 /* Insert the positions of one tile into level K's table, in order, and record
- * for each the distance to the previous position of the same slot (0 = none in
- * the window).  Executed by one whole warp. */
+ * for each the distance to the previous position of the same slot (0 = none within
+ * 2047).  Executed by one whole warp; vt = virtual position of the tile start, a multiple
+ * of 32.  The last batch of a stream runs all 32 lanes: the positions past the end sit in
+ * the gap before the next stream, where no query ever looks (a candidate is valid only up
+ * to the query's own position inside its stream). */
 template <int K>
 __device__ __forceinline__ void k1_build_level(uint16_t *heads, uint16_t *links, const uint32_t *W,
-                                               uint32_t v0, uint32_t t0, uint32_t tile_n)
+                                               uint32_t vt, uint32_t tile_n)
 {
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
-    uint16_t      *hd = heads + (K - 2) * kK1Slots;
-    uint16_t      *lk = links + (K - 2) * kK1LinkRing;
-    uint32_t       hnext = k1_hash_at<K>(W, v0 + t0 + lane);
+    uint16_t       *hd = heads + (K - 2) * kK1Slots;
+    uint16_t       *lk = links + (K - 2) * kK1LinkRing + lane;
+    const uint32_t *Wl = W + lane;
+    uint32_t        hnext = k1_hash_at<K>(Wl, vt & (kK1WRing - 1));
     for (uint32_t b = 0; b < tile_n; b += 32) {
-        const uint32_t i = t0 + b + lane;
-        const uint32_t v = v0 + i;
-        const bool     act = (b + lane) < tile_n;
-        const uint32_t pos16 = v & 0xFFFFu;
-        const uint32_t cur = hnext >> kSlotShift;
-        const uint32_t tag = (hnext >> kTagShift) & 31u;
-        hnext = k1_hash_at<K>(W, v + 32);    /* next batch: independent of the table, overlaps below */
+        const uint32_t vb = vt + b;                       /* warp-uniform, a multiple of 32 */
+        const uint32_t pos16 = (vb & 0xFFFFu) | lane;
+        const uint32_t h = hnext;
+        uint16_t      *slot = hd + (h >> kSlotShift);
+        hnext = k1_hash_at<K>(Wl, (vb + 32) & (kK1WRing - 1));   /* next batch: independent of the table */
 
-        const uint32_t old = act ? hd[cur] : 0u;
+        const uint32_t old = *slot;
         __syncwarp();                        /* every lane has the pre-batch head       */
-        if (act) hd[cur] = static_cast<uint16_t>(pos16);
+        *slot = static_cast<uint16_t>(pos16);
         __syncwarp();
-        const uint32_t back = act ? hd[cur] : pos16;
+        const uint32_t back = *slot;
         const bool     loser = back != pos16; /* another lane of this batch owns my slot */
-        uint32_t       dist = (pos16 - old) & 0xFFFFu;
-        if (__ballot_sync(LZS_FULL_MASK, loser) != 0u) {
-            /* order the duplicated lanes only: the slot's winner and its losers */
-            const uint32_t base16 = (v0 + t0 + b) & 0xFFFFu;
-            const uint32_t named =
-                __reduce_or_sync(LZS_FULL_MASK, loser ? (1u << ((back - base16) & 31u)) : 0u);
-            const bool     dup = act && (loser || ((named >> lane) & 1u));
-            const uint32_t grp = __match_any_sync(LZS_FULL_MASK, dup ? cur : 0xFFFFFFFFu);
+        uint32_t       dist = pos16 - old;    /* its low 16 bits are the distance        */
+        if (__any_sync(LZS_FULL_MASK, loser)) {
+            /* order the duplicated lanes only: the slot's winner (lane = back & 31) and its losers */
+            const uint32_t named = __reduce_or_sync(LZS_FULL_MASK, loser ? (1u << (back & 31u)) : 0u);
+            const bool     dup = loser || ((named >> lane) & 1u);
+            const uint32_t grp = __match_any_sync(LZS_FULL_MASK, dup ? (h >> kSlotShift) : 0xFFFFFFFFu);
             if (dup) {
                 const uint32_t lower = grp & lt;
                 if (lower) dist = lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(lower))));
-                if ((grp >> lane) == 1u && loser) hd[cur] = static_cast<uint16_t>(pos16);  /* last one owns the head */
+                if ((grp >> lane) == 1u && loser) *slot = static_cast<uint16_t>(pos16);  /* last one owns the head */
             }
             __syncwarp();
         }
-        if (act) {
-            if (dist > umin32(kWindow, i)) dist = 0;
-            lk[v & (kK1LinkRing - 1)] = static_cast<uint16_t>(dist | (tag << 11));
-        }
+        uint32_t e = (h >> (kTagShift - 11)) & 0xF800u;   /* tag << 11 */
+        if ((dist & 0xF800u) == 0u) e |= dist & kLinkDistMask;   /* further than the window: no link */
+        lk[vb & (kK1LinkRing - 1)] = static_cast<uint16_t>(e);
     }
 }
 
@@ -253,9 +249,8 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
     const uint32_t maxd = umin32(kWindow, i);
     if (M < kMinLen || maxd == 0) return 0;
     const uint32_t v = v0 + i;
-    const uint32_t w0 = W[v & (kK1WRing - 1)];
-    const uint32_t w1 = W[(v + 4) & (kK1WRing - 1)];
-    const uint32_t w2 = W[(v + 8) & (kK1WRing - 1)];
+    const uint32_t *wv = W + (v & (kK1WRing - 1));           /* the mirror covers +4 and +8 */
+    const uint32_t w0 = wv[0], w1 = wv[4], w2 = wv[8];
     uint32_t best = 0, bd = 0;
     uint32_t k = kMinLen;
     const uint16_t *lk = links;                              /* level k's ring              */
@@ -287,8 +282,8 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
             }
             continue;
         }
-        const uint32_t l = umin32(lcp12(w0, w1, w2, W[j & (kK1WRing - 1)], W[(j + 4) & (kK1WRing - 1)],
-                                        W[(j + 8) & (kK1WRing - 1)]), M);
+        const uint32_t *wj = W + (j & (kK1WRing - 1));
+        const uint32_t l = umin32(lcp12(w0, w1, w2, wj[0], wj[4], wj[8]), M);
         if (l < k) { LZS_STAT(3, 1); continue; }
         LZS_STAT(4, 1);
         best = l;                                            /* nearest candidate of length l */
@@ -338,37 +333,68 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             const uint8_t *src = in + in_off[sid];
             const uint8_t *end = src + n;
             const uint32_t v0 = vnext;
-            vnext = v0 + n + kK1StreamGap;
+            vnext = (v0 + n + 16u + 31u) & ~31u;
 
             for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
                 const uint32_t buf = g & 1u;
                 const uint32_t tile_n = umin32(kK1Tile, n - t0);
-                /* 4-byte grams of the new positions, kK1Ahead beyond the tile: 8 for the 12-byte
-                 * compares plus the 32 positions whose hashes the build warps prefetch in their
-                 * last batch (so a warp that is already filling the next tile never writes a gram
-                 * a slower warp still reads).  Done BEFORE waiting for the query group: the gram
-                 * ring is large enough that these slots are free, so the global-load latency
-                 * hides in that wait. */
-                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + kK1Ahead;
-                const uint32_t p_hi = umin32(t0 + kK1Tile + kK1Ahead, n + 12u);
-                for (uint32_t p = p_lo + tid; p < p_hi; p += kK1BuildThreads)
-                    W[(v0 + p) & (kK1WRing - 1)] = (p < n) ? load4_unaligned(src + p, end) : 0u;
+                /* 4-byte grams are kept kK1Ahead positions beyond the tile being built: 8 for the
+                 * 12-byte compares plus the 32 positions whose hashes the build warps prefetch in
+                 * their last batch.  The first tile of a stream is filled here; for every later
+                 * tile the global loads are issued now, fly during this tile's build, and are
+                 * written to the ring after it (no build or query warp reads those slots yet, and
+                 * the ring is large enough that they are free). */
+                if (t0 == 0) {
+                    const uint32_t p_hi = umin32(kK1Tile + kK1Ahead, n + 12u);
+                    for (uint32_t p = tid; p < p_hi; p += kK1BuildThreads) {
+                        const uint32_t x = (v0 + p) & (kK1WRing - 1);
+                        const uint32_t w = (p < n) ? load4_unaligned(src + p, end) : 0u;
+                        W[x] = w;
+                        if (x < kK1WMirror) W[kK1WRing + x] = w;
+                    }
+                }
+                const uint32_t q_lo = t0 + kK1Tile + kK1Ahead;
+                const uint32_t q_hi = (t0 + kK1Tile < n) ? umin32(q_lo + kK1Tile, n + 12u) : q_lo;
+                const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src + q_lo + tid) & 3u) * 8u;
+                uint32_t       glo[kK1FillPerThread], ghi[kK1FillPerThread];
+#pragma unroll
+                for (int j = 0; j < kK1FillPerThread; j++) {
+                    const uint32_t p = q_lo + tid + static_cast<uint32_t>(j) * kK1BuildThreads;
+                    glo[j] = 0u;
+                    ghi[j] = 0u;
+                    if (p < q_hi && p < n) {
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(
+                            reinterpret_cast<uintptr_t>(src + p) & ~static_cast<uintptr_t>(3));
+                        if (reinterpret_cast<const uint8_t *>(w) < end) glo[j] = __ldg(w);
+                        if (sh != 0u && reinterpret_cast<const uint8_t *>(w + 1) < end) ghi[j] = __ldg(w + 1);
+                    }
+                }
                 if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
                 named_sync(kBarBuild, kK1BuildThreads);
 
                 switch (warp) {
-                    case 0:  k1_build_level<2>(heads, links, W, v0, t0, tile_n); break;
-                    case 1:  k1_build_level<3>(heads, links, W, v0, t0, tile_n); break;
-                    case 2:  k1_build_level<4>(heads, links, W, v0, t0, tile_n); break;
-                    case 3:  k1_build_level<5>(heads, links, W, v0, t0, tile_n); break;
-                    case 4:  k1_build_level<6>(heads, links, W, v0, t0, tile_n); break;
-                    case 5:  k1_build_level<7>(heads, links, W, v0, t0, tile_n); break;
-                    case 6:  k1_build_level<8>(heads, links, W, v0, t0, tile_n); break;
-                    case 7:  k1_build_level<9>(heads, links, W, v0, t0, tile_n); break;
-                    case 8:  k1_build_level<10>(heads, links, W, v0, t0, tile_n); break;
-                    case 9:  k1_build_level<11>(heads, links, W, v0, t0, tile_n); break;
-                    case 10: k1_build_level<12>(heads, links, W, v0, t0, tile_n); break;
+                    case 0:  k1_build_level<2>(heads, links, W, v0 + t0, tile_n); break;
+                    case 1:  k1_build_level<3>(heads, links, W, v0 + t0, tile_n); break;
+                    case 2:  k1_build_level<4>(heads, links, W, v0 + t0, tile_n); break;
+                    case 3:  k1_build_level<5>(heads, links, W, v0 + t0, tile_n); break;
+                    case 4:  k1_build_level<6>(heads, links, W, v0 + t0, tile_n); break;
+                    case 5:  k1_build_level<7>(heads, links, W, v0 + t0, tile_n); break;
+                    case 6:  k1_build_level<8>(heads, links, W, v0 + t0, tile_n); break;
+                    case 7:  k1_build_level<9>(heads, links, W, v0 + t0, tile_n); break;
+                    case 8:  k1_build_level<10>(heads, links, W, v0 + t0, tile_n); break;
+                    case 9:  k1_build_level<11>(heads, links, W, v0 + t0, tile_n); break;
+                    case 10: k1_build_level<12>(heads, links, W, v0 + t0, tile_n); break;
                     default: k1_build_runs(runs, W, v0, t0, tile_n); break;
+                }
+#pragma unroll
+                for (int j = 0; j < kK1FillPerThread; j++) {
+                    const uint32_t p = q_lo + tid + static_cast<uint32_t>(j) * kK1BuildThreads;
+                    if (p < q_hi) {
+                        const uint32_t x = (v0 + p) & (kK1WRing - 1);
+                        const uint32_t w = __funnelshift_r(glo[j], ghi[j], sh);
+                        W[x] = w;
+                        if (x < kK1WMirror) W[kK1WRing + x] = w;
+                    }
                 }
                 if (tid == 0) {
                     K1Tile d;

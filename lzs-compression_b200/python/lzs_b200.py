@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "liblzs.so")
+# LZS_B200_LIB selects another build of the same library (kernel variants in tools/ experiments)
+LIB_PATH = os.environ.get("LZS_B200_LIB") or os.path.join(PKG_DIR, "liblzs.so")
 
 u8p = ctypes.POINTER(ctypes.c_uint8)
 u16p = ctypes.POINTER(ctypes.c_uint16)
