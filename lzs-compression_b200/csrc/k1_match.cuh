@@ -81,7 +81,9 @@ constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the 
 #define LZS_K1_QW 16
 #endif
 constexpr int      kK1QueryWarps = LZS_K1_QW;
-constexpr int      kK1Threads = 32 * (kK1BuildWarps + kK1QueryWarps);
+constexpr int      kK1Threads = 32 * (kK1BuildWarps + 1 + kK1QueryWarps);   /* + the loader warp */
+constexpr unsigned kK1PipeThreads = 32 * (kK1BuildWarps + kK1QueryWarps);  /* members of the tile hand-off barriers */
+constexpr int      kK1LoadUnroll = 8;       /* global loads in flight per loader lane */
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
 constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 +
@@ -91,11 +93,9 @@ constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 
 constexpr uint32_t kRunBackMask = 0xFFFu;
 static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
 constexpr uint32_t kK1Ahead = 40;           /* grams filled beyond the tile being built */
-constexpr int      kK1FillPerThread = static_cast<int>((kK1Tile + kK1BuildThreads - 1) / kK1BuildThreads);
-static_assert(kK1BuildThreads % 4 == 0, "one byte shift per thread for all its gram loads");
-static_assert(kWindow + 3 * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring must hold one tile more than the links");
+static_assert(kWindow + 4 * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring: window + two tiles in the pipeline + two the loader may be ahead");
 
-enum { kBarBuild = 1, kBarFull0 = 2, kBarFull1 = 3, kBarEmpty0 = 4, kBarEmpty1 = 5 };
+enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4 };
 constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
 
 struct K1Tile {
@@ -163,6 +163,7 @@ __device__ __forceinline__ void k1_build_level(uint16_t *heads, uint16_t *links,
     uint16_t       *lk = links + (K - 2) * kK1LinkRing + lane;
     const uint32_t *Wl = W + lane;
     uint32_t        hnext = k1_hash_at<K>(Wl, vt & (kK1WRing - 1));
+#pragma unroll 1   /* eleven specialised copies of this loop run side by side: keep them small for the instruction cache */
     for (uint32_t b = 0; b < tile_n; b += 32) {
         const uint32_t vb = vt + b;                       /* warp-uniform, a multiple of 32 */
         const uint32_t pos16 = (vb & 0xFFFFu) | lane;
@@ -204,28 +205,30 @@ __device__ __forceinline__ void k1_build_level(uint16_t *heads, uint16_t *links,
 __device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W, uint32_t v0, uint32_t t0,
                                               uint32_t tile_n)
 {
-    const uint32_t lane = lane_id();
+    const uint32_t  lane = lane_id();
+    const uint32_t  vt = v0 + t0;                         /* a multiple of 32 */
+    const uint32_t *Wl = W + lane;
+    uint16_t       *rl = runs + lane;
+    /* carried from batch to batch in registers: the byte before the batch and how far back its run starts */
+    uint32_t prev_byte = (t0 == 0) ? 0x100u : (W[(vt - 1u) & (kK1WRing - 1)] & 0xFFu);
+    uint32_t carry = (t0 == 0) ? 0u : (runs[(vt - 1u) & (kK1LinkRing - 1)] & kRunBackMask);
+#pragma unroll 1
     for (uint32_t b = 0; b < tile_n; b += 32) {
-        const uint32_t i = t0 + b + lane;
-        const uint32_t v = v0 + i;
-        const bool     act = (b + lane) < tile_n;
-        const uint32_t w0 = W[v & (kK1WRing - 1)], w1 = W[(v + 4) & (kK1WRing - 1)], w2 = W[(v + 8) & (kK1WRing - 1)];
-        const uint32_t rep = (w0 & 0xFFu) * 0x01010101u;
+        const uint32_t vb = vt + b;
+        const uint32_t x = vb & (kK1WRing - 1);
+        const uint32_t w0 = Wl[x], w1 = Wl[x + 4], w2 = Wl[x + 8];
+        const uint32_t byte = w0 & 0xFFu;
+        const uint32_t rep = byte * 0x01010101u;
         const uint32_t fwd = lcp12(w0, w1, w2, rep, rep, rep);                 /* 1..12 */
-        const uint32_t prev = (i == 0) ? 0x100u : (W[(v - 1) & (kK1WRing - 1)] & 0xFFu);   /* byte i-1 */
-        const bool     start = !act || prev != (w0 & 0xFFu);                   /* p begins a run */
-        const uint32_t starts = __ballot_sync(LZS_FULL_MASK, start);
+        uint32_t       before = __shfl_up_sync(LZS_FULL_MASK, byte, 1);
+        if (lane == 0) before = prev_byte;
+        const uint32_t starts = __ballot_sync(LZS_FULL_MASK, before != byte);  /* positions that begin a run */
         const uint32_t below = starts & ((2u << lane) - 1u);                   /* starts at or below my lane */
-        uint32_t       back;
-        if (below) {
-            back = lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(below))));
-        } else {                                                               /* the run began in an earlier batch */
-            const uint32_t carry = runs[(v0 + t0 + b - 1u) & (kK1LinkRing - 1)] & kRunBackMask;
-            back = umin32(carry + lane + 1u, kRunBackMask);
-        }
-        __syncwarp();
-        if (act) runs[v & (kK1LinkRing - 1)] = static_cast<uint16_t>((fwd << 12) | back);
-        __syncwarp();
+        const uint32_t back = below ? lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(below))))
+                                    : umin32(carry + lane + 1u, kRunBackMask);  /* the run began in an earlier batch */
+        rl[vb & (kK1LinkRing - 1)] = static_cast<uint16_t>((fwd << 12) | back);
+        carry = __shfl_sync(LZS_FULL_MASK, back, 31);
+        prev_byte = __shfl_sync(LZS_FULL_MASK, byte, 31);
     }
 }
 
@@ -309,119 +312,139 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     uint16_t *links = heads + kK1Levels * kK1Slots;
     uint16_t *runs = links + kK1Levels * kK1LinkRing;
     uint32_t *W = reinterpret_cast<uint32_t *>(runs + kK1LinkRing);
-    __shared__ uint32_t s_sid;
-    __shared__ K1Tile   s_tile[2];
+    __shared__ K1Tile   s_desc[4];           /* tile g is described in s_desc[g & 3]             */
+    __shared__ uint32_t s_filled;            /* tiles whose grams and descriptor are in place     */
+    __shared__ uint32_t s_qdone;             /* query-warp completions: tile q is done at 16(q+1) */
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
+    const uint32_t lane = tid & 31u;
 
     for (uint32_t x = tid; x < kK1Levels * (kK1Slots + kK1LinkRing) + kK1LinkRing; x += kK1Threads) heads[x] = 0;
+    if (tid == 0) { s_filled = 0; s_qdone = 0; }
     __syncthreads();
 
-    if (warp < static_cast<uint32_t>(kK1BuildWarps)) {
-        /* ================= producer: fill grams, build the 11 levels ================= */
-        uint32_t g = 0;                      /* tiles produced so far                   */
+    if (warp == static_cast<uint32_t>(kK1BuildWarps)) {
+        /* ================= loader: streams -> tiles, 4-byte grams into the ring =================
+         * Runs ahead of the build warps (up to three tiles ahead of the query group, which is what
+         * the gram ring holds), so the global-load latency is off everybody's critical path and
+         * the build warps never have to meet each other. */
+        uint32_t g = 0;                      /* tiles described so far                  */
         uint32_t vnext = 4096;               /* virtual position of the next stream     */
         for (;;) {
-            if (tid == 0) s_sid = atomicAdd(next_stream, 1u);
-            named_sync(kBarBuild, kK1BuildThreads);
-            const uint32_t sid = s_sid;
-            named_sync(kBarBuild, kK1BuildThreads);
+            uint32_t sid = 0;
+            if (lane == 0) sid = atomicAdd(next_stream, 1u);
+            sid = __shfl_sync(LZS_FULL_MASK, sid, 0);
             if (sid >= n_streams) break;
-
             const uint32_t n = in_len[sid];
             const uint8_t *src = in + in_off[sid];
-            const uint8_t *end = src + n;
+            /* last aligned word that holds a byte of the stream (n > 0 inside the tile loop) */
+            const uintptr_t wlast = (reinterpret_cast<uintptr_t>(src) + (n ? n - 1u : 0u)) & ~static_cast<uintptr_t>(3);
             const uint32_t v0 = vnext;
             vnext = (v0 + n + 16u + 31u) & ~31u;
-
             for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
-                const uint32_t buf = g & 1u;
-                const uint32_t tile_n = umin32(kK1Tile, n - t0);
-                /* 4-byte grams are kept kK1Ahead positions beyond the tile being built: 8 for the
-                 * 12-byte compares plus the 32 positions whose hashes the build warps prefetch in
-                 * their last batch.  The first tile of a stream is filled here; for every later
-                 * tile the global loads are issued now, fly during this tile's build, and are
-                 * written to the ring after it (no build or query warp reads those slots yet, and
-                 * the ring is large enough that they are free). */
-                if (t0 == 0) {
-                    const uint32_t p_hi = umin32(kK1Tile + kK1Ahead, n + 12u);
-                    for (uint32_t p = tid; p < p_hi; p += kK1BuildThreads) {
-                        const uint32_t x = (v0 + p) & (kK1WRing - 1);
-                        const uint32_t w = (p < n) ? load4_unaligned(src + p, end) : 0u;
-                        W[x] = w;
-                        if (x < kK1WMirror) W[kK1WRing + x] = w;
-                    }
+                /* byte shift of this lane's grams: the same for every step (steps are multiples of 32) */
+                const uint32_t sh = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(src) + lane +
+                                                           ((t0 == 0) ? 0u : t0 + kK1Ahead)) & 3u) * 8u;
+                if (g >= 3) {
+                    while (*reinterpret_cast<volatile uint32_t *>(&s_qdone) < (g - 2u) * kK1QueryWarps) spin_pause();
+                    __threadfence_block();
                 }
-                const uint32_t q_lo = t0 + kK1Tile + kK1Ahead;
-                const uint32_t q_hi = (t0 + kK1Tile < n) ? umin32(q_lo + kK1Tile, n + 12u) : q_lo;
-                const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src + q_lo + tid) & 3u) * 8u;
-                uint32_t       glo[kK1FillPerThread], ghi[kK1FillPerThread];
+                /* grams are kept kK1Ahead positions beyond the tile: 8 for the 12-byte compares plus
+                 * the 32 positions whose hashes the build warps prefetch in their last batch */
+                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + kK1Ahead;
+                const uint32_t p_hi = umin32(t0 + kK1Tile + kK1Ahead, n + 12u);
+                for (uint32_t pb = p_lo; pb < p_hi; pb += 32u * kK1LoadUnroll) {
+                    /* branch-free (addresses clamped to the stream's last aligned word), so that
+                     * all the loads of a step are in flight together */
+                    uint32_t lo[kK1LoadUnroll], hi[kK1LoadUnroll], w[kK1LoadUnroll];
 #pragma unroll
-                for (int j = 0; j < kK1FillPerThread; j++) {
-                    const uint32_t p = q_lo + tid + static_cast<uint32_t>(j) * kK1BuildThreads;
-                    glo[j] = 0u;
-                    ghi[j] = 0u;
-                    if (p < q_hi && p < n) {
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>(
-                            reinterpret_cast<uintptr_t>(src + p) & ~static_cast<uintptr_t>(3));
-                        if (reinterpret_cast<const uint8_t *>(w) < end) glo[j] = __ldg(w);
-                        if (sh != 0u && reinterpret_cast<const uint8_t *>(w + 1) < end) ghi[j] = __ldg(w + 1);
+                    for (int j = 0; j < kK1LoadUnroll; j++) {
+                        const uint32_t  q = pb + static_cast<uint32_t>(j) * 32u + lane;
+                        const uintptr_t a = (reinterpret_cast<uintptr_t>(src) + q) & ~static_cast<uintptr_t>(3);
+                        lo[j] = __ldg(reinterpret_cast<const uint32_t *>(a < wlast ? a : wlast));
+                        hi[j] = __ldg(reinterpret_cast<const uint32_t *>(a + 4 < wlast ? a + 4 : wlast));
                     }
-                }
-                if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
-                named_sync(kBarBuild, kK1BuildThreads);
-
-                switch (warp) {
-                    case 0:  k1_build_level<2>(heads, links, W, v0 + t0, tile_n); break;
-                    case 1:  k1_build_level<3>(heads, links, W, v0 + t0, tile_n); break;
-                    case 2:  k1_build_level<4>(heads, links, W, v0 + t0, tile_n); break;
-                    case 3:  k1_build_level<5>(heads, links, W, v0 + t0, tile_n); break;
-                    case 4:  k1_build_level<6>(heads, links, W, v0 + t0, tile_n); break;
-                    case 5:  k1_build_level<7>(heads, links, W, v0 + t0, tile_n); break;
-                    case 6:  k1_build_level<8>(heads, links, W, v0 + t0, tile_n); break;
-                    case 7:  k1_build_level<9>(heads, links, W, v0 + t0, tile_n); break;
-                    case 8:  k1_build_level<10>(heads, links, W, v0 + t0, tile_n); break;
-                    case 9:  k1_build_level<11>(heads, links, W, v0 + t0, tile_n); break;
-                    case 10: k1_build_level<12>(heads, links, W, v0 + t0, tile_n); break;
-                    default: k1_build_runs(runs, W, v0, t0, tile_n); break;
-                }
 #pragma unroll
-                for (int j = 0; j < kK1FillPerThread; j++) {
-                    const uint32_t p = q_lo + tid + static_cast<uint32_t>(j) * kK1BuildThreads;
-                    if (p < q_hi) {
-                        const uint32_t x = (v0 + p) & (kK1WRing - 1);
-                        const uint32_t w = __funnelshift_r(glo[j], ghi[j], sh);
-                        W[x] = w;
-                        if (x < kK1WMirror) W[kK1WRing + x] = w;
+                    for (int j = 0; j < kK1LoadUnroll; j++) {
+                        const uint32_t  q = pb + static_cast<uint32_t>(j) * 32u + lane;
+                        const uintptr_t a = (reinterpret_cast<uintptr_t>(src) + q) & ~static_cast<uintptr_t>(3);
+                        const uint32_t  h = (a + 4 <= wlast) ? hi[j] : 0u;     /* word beyond the stream: zero */
+                        w[j] = (q < n) ? __funnelshift_r(lo[j], h, sh) : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kK1LoadUnroll; j++) {
+                        const uint32_t q = pb + static_cast<uint32_t>(j) * 32u + lane;
+                        if (q < p_hi) {
+                            const uint32_t x = (v0 + q) & (kK1WRing - 1);
+                            W[x] = w[j];
+                            if (x < kK1WMirror) W[kK1WRing + x] = w[j];
+                        }
                     }
                 }
-                if (tid == 0) {
+                if (lane == 0) {
                     K1Tile d;
-                    d.sid = sid; d.t0 = t0; d.tile_n = tile_n; d.n = n; d.v0 = v0;
-                    s_tile[buf] = d;
+                    d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0;
+                    s_desc[g & 3u] = d;
                 }
-                named_arrive(kBarFull0 + static_cast<int>(buf), kK1Threads);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_filled) = g + 1u;
             }
         }
-        const uint32_t buf = g & 1u;
-        if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
-        if (tid == 0) s_tile[buf].sid = kK1EndOfWork;
-        named_arrive(kBarFull0 + static_cast<int>(buf), kK1Threads);
-    } else {
-        /* ================= consumer: one query per position ================= */
-        const uint32_t qtid = tid - kK1BuildThreads;
+        if (g >= 3) {
+            while (*reinterpret_cast<volatile uint32_t *>(&s_qdone) < (g - 2u) * kK1QueryWarps) spin_pause();
+        }
+        if (lane == 0) s_desc[g & 3u].sid = kK1EndOfWork;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_filled) = g + 1u;
+    } else if (warp < static_cast<uint32_t>(kK1BuildWarps)) {
+        /* ================= build warps: one level each (the twelfth: the run table) =================
+         * Independent of each other: a warp waits for the loader (flag), for the query group to
+         * have left the tile two back (named barrier), builds, and signals the query group. */
         for (uint32_t g = 0;; g++) {
             const uint32_t buf = g & 1u;
-            named_sync(kBarFull0 + static_cast<int>(buf), kK1Threads);
-            const K1Tile d = s_tile[buf];
+            while (*reinterpret_cast<volatile uint32_t *>(&s_filled) <= g) spin_pause();
+            __threadfence_block();
+            const K1Tile d = s_desc[g & 3u];
+            if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1PipeThreads);
+            if (d.sid != kK1EndOfWork) {
+                const uint32_t vt = d.v0 + d.t0;
+                switch (warp) {
+                    case 0:  k1_build_level<2>(heads, links, W, vt, d.tile_n); break;
+                    case 1:  k1_build_level<3>(heads, links, W, vt, d.tile_n); break;
+                    case 2:  k1_build_level<4>(heads, links, W, vt, d.tile_n); break;
+                    case 3:  k1_build_level<5>(heads, links, W, vt, d.tile_n); break;
+                    case 4:  k1_build_level<6>(heads, links, W, vt, d.tile_n); break;
+                    case 5:  k1_build_level<7>(heads, links, W, vt, d.tile_n); break;
+                    case 6:  k1_build_level<8>(heads, links, W, vt, d.tile_n); break;
+                    case 7:  k1_build_level<9>(heads, links, W, vt, d.tile_n); break;
+                    case 8:  k1_build_level<10>(heads, links, W, vt, d.tile_n); break;
+                    case 9:  k1_build_level<11>(heads, links, W, vt, d.tile_n); break;
+                    case 10: k1_build_level<12>(heads, links, W, vt, d.tile_n); break;
+                    default: k1_build_runs(runs, W, d.v0, d.t0, d.tile_n); break;
+                }
+            }
+            named_arrive(kBarFull0 + static_cast<int>(buf), kK1PipeThreads);
+            if (d.sid == kK1EndOfWork) break;
+        }
+    } else {
+        /* ================= query warps: one query per position ================= */
+        const uint32_t qtid = tid - 32u * (kK1BuildWarps + 1);
+        for (uint32_t g = 0;; g++) {
+            const uint32_t buf = g & 1u;
+            named_sync(kBarFull0 + static_cast<int>(buf), kK1PipeThreads);
+            const K1Tile d = s_desc[g & 3u];
             if (d.sid == kK1EndOfWork) break;
             match_t *mout = matches + in_off[d.sid];
             for (uint32_t r = qtid; r < d.tile_n; r += kK1QueryThreads) {
                 const uint32_t i = d.t0 + r;
                 mout[i] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
             }
-            named_arrive(kBarEmpty0 + static_cast<int>(buf), kK1Threads);
+            named_arrive(kBarEmpty0 + static_cast<int>(buf), kK1PipeThreads);
+            __syncwarp();
+            if (lane == 0) atomicAdd(&s_qdone, 1u);      /* the loader may reuse the ring behind us */
         }
     }
 }

@@ -59,6 +59,16 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t *p, const uint
     return __funnelshift_r(lo, hi, sh);
 }
 
+/* Body of a spin-wait on a shared-memory flag. */
+__device__ __forceinline__ void spin_pause()
+{
+#ifdef LZS_SIMT_EMU
+    simt_yield();
+#else
+    __nanosleep(20);
+#endif
+}
+
 /* Named barriers (PTX bar.sync / bar.arrive): `count` threads take part in total;
  * sync waits for all of them, arrive only signals.  Used for producer/consumer
  * hand-off between warp groups of one CTA. */
