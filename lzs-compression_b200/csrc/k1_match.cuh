@@ -64,14 +64,18 @@
 namespace lzs {
 
 constexpr int      kK1Levels = 11;          /* k = 2 .. 12 */
-constexpr uint32_t kK1Slots = 4096;
+constexpr uint32_t kK1Slots = 2048;          /* 32-bit heads (exchanged atomically) */
 constexpr uint32_t kK1LinkRing = 4096;      /* >= 2047 + 2 * (tile + gap)          */
 constexpr uint32_t kK1WRing = 8192;
 constexpr uint32_t kK1WMirror = 64;         /* the first grams again behind the ring: index, +4, +8 need one wrap */
 #ifndef LZS_K1_TILE
-#define LZS_K1_TILE 960
+#define LZS_K1_TILE 448
 #endif
-constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 960 = 30 batches  */
+#ifndef LZS_K1_DEPTH
+#define LZS_K1_DEPTH 4
+#endif
+constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 448 = 14 batches  */
+constexpr uint32_t kK1Depth = LZS_K1_DEPTH; /* tiles the build warps may be ahead of the query group (power of two) */
 /* Virtual positions between streams: 12 zero grams behind the last byte, then up to the next
  * multiple of 32 (every stream starts on a batch boundary, so a batch never straddles a ring
  * wrap and the positions a last batch inserts past the end of its stream belong to no stream). */
@@ -82,20 +86,19 @@ constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the 
 #endif
 constexpr int      kK1QueryWarps = LZS_K1_QW;
 constexpr int      kK1Threads = 32 * (kK1BuildWarps + 1 + kK1QueryWarps);   /* + the loader warp */
-constexpr unsigned kK1PipeThreads = 32 * (kK1BuildWarps + kK1QueryWarps);  /* members of the tile hand-off barriers */
 constexpr int      kK1LoadUnroll = 8;       /* global loads in flight per loader lane */
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
-constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 2 +
+constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 4 +
                                 static_cast<size_t>(kK1Levels + 1) * kK1LinkRing * 2 +
                                 (kK1WRing + kK1WMirror) * 4;
 /* run table entry: (forward run length capped at 12) << 12 | distance back to the run start */
 constexpr uint32_t kRunBackMask = 0xFFFu;
-static_assert(kWindow + 2 * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
+static_assert((kK1Depth & (kK1Depth - 1)) == 0 && kK1Depth >= 2 && kK1Depth <= 4, "pipeline depth");
+static_assert(kWindow + kK1Depth * (kK1Tile + kK1StreamGap) < kK1LinkRing, "link ring too small for the pipeline");
 constexpr uint32_t kK1Ahead = 40;           /* grams filled beyond the tile being built */
-static_assert(kWindow + 4 * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring: window + two tiles in the pipeline + two the loader may be ahead");
+static_assert(kWindow + (kK1Depth + 2) * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring: window + the tiles in the pipeline + those the loader may be ahead");
 
-enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4 };
 constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
 
 struct K1Tile {
@@ -125,19 +128,20 @@ __device__ __forceinline__ uint32_t gram_hash_c(uint32_t w0, uint32_t w1, uint32
     h *= 0x27D4EB2Fu;
     return h;
 }
-constexpr uint32_t kSlotShift = 20;          /* slot = h >> 20 (12 bits)                    */
+constexpr uint32_t kSlotShift = 21;          /* slot = h >> 21 (11 bits)                    */
 constexpr uint32_t kTagShift = 15;           /* tag  = (h >> 15) & 31                       */
 constexpr uint32_t kLinkDistMask = 0x7FFu;   /* link entry: (tag << 11) | distance          */
 
-/* common prefix length (0..12) of two 12-byte strings given as LE words */
+/* common prefix length (0..12) of two 12-byte strings given as LE words; branch-free, so the
+ * lanes of a warp stay together whatever the data */
 __device__ __forceinline__ uint32_t lcp12(uint32_t a0, uint32_t a1, uint32_t a2,
                                           uint32_t b0, uint32_t b1, uint32_t b2)
 {
     const uint32_t x0 = a0 ^ b0, x1 = a1 ^ b1, x2 = a2 ^ b2;
-    if (x0) return static_cast<uint32_t>(__ffs(static_cast<int>(x0)) - 1) >> 3;
-    if (x1) return 4u + (static_cast<uint32_t>(__ffs(static_cast<int>(x1)) - 1) >> 3);
-    if (x2) return 8u + (static_cast<uint32_t>(__ffs(static_cast<int>(x2)) - 1) >> 3);
-    return 12u;
+    /* first differing word, and 4 x its index; the sentinel bit makes "all equal" come out as 12 */
+    const uint32_t x = x0 ? x0 : (x1 ? x1 : (x2 ? x2 : 1u));
+    const uint32_t base = x0 ? 0u : (x1 ? 4u : 8u + ((x2 == 0u) ? 4u : 0u));
+    return base + (static_cast<uint32_t>(__ffs(static_cast<int>(x)) - 1) >> 3);
 }
 
 /* hash of the K-gram at gram-ring index x (x < kK1WRing; the mirror covers x + 8) */
@@ -147,51 +151,69 @@ __device__ __forceinline__ uint32_t k1_hash_at(const uint32_t *W, uint32_t x)
     return gram_hash_c<K>(W[x], K > 4 ? W[x + 4] : 0u, K > 8 ? W[x + 8] : 0u);
 }
 
-/* Insert the positions of one tile into level K's table, in order, and record
- * for each the distance to the previous position of the same slot (0 = none within
- * 2047).  Executed by one whole warp; vt = virtual position of the tile start, a multiple
- * of 32.  The last batch of a stream runs all 32 lanes: the positions past the end sit in
- * the gap before the next stream, where no query ever looks (a candidate is valid only up
- * to the query's own position inside its stream). */
-template <int K>
-__device__ __forceinline__ void k1_build_level(uint16_t *heads, uint16_t *links, const uint32_t *W,
-                                               uint32_t vt, uint32_t tile_n)
+/* Exchange on a shared-memory word: returns the previous value. */
+__device__ __forceinline__ uint32_t smem_exch(uint32_t *p, uint32_t v)
+{
+#ifdef LZS_SIMT_EMU
+    return atomicExch(p, v);
+#else
+    uint32_t o;
+    asm volatile("atom.shared.exch.b32 %0, [%1], %2;"
+                 : "=r"(o)
+                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))), "r"(v)
+                 : "memory");
+    return o;
+#endif
+}
+
+/* Exact repair of one batch's exchanges, for the case that the lanes sharing a slot were not
+ * served in ascending lane order (sm_100a serves them in ascending order --
+ * tools/micro/atoms_exch.cu -- so this is insurance, exercised by the emulator tests).
+ * Whatever the order, exactly one lane of every group received the pre-batch head.  Returns the
+ * position each lane should have received and leaves the group's highest lane in the head. */
+__device__ __noinline__ uint32_t k1_relink(uint32_t *slot, uint32_t key, uint32_t old, uint32_t vb, uint32_t pos)
 {
     const uint32_t lane = lane_id();
-    const uint32_t lt = (1u << lane) - 1u;
-    uint16_t       *hd = heads + (K - 2) * kK1Slots;
+    const uint32_t grp = __match_any_sync(LZS_FULL_MASK, key);
+    const uint32_t lower = grp & ((1u << lane) - 1u);
+    const uint32_t outside = __ballot_sync(LZS_FULL_MASK, (old - vb) >= 32u);
+    const uint32_t pre = __shfl_sync(LZS_FULL_MASK, old, __ffs(static_cast<int>(grp & outside)) - 1);
+    if ((grp >> lane) == 1u) *slot = pos;
+    __syncwarp();
+    return lower ? (vb | (31u - static_cast<uint32_t>(__clz(static_cast<int>(lower))))) : pre;
+}
+
+/* Insert the positions of one tile into level K's table, in order, and record for each the
+ * distance to the previous position of the same slot (0 = none within 2047).  Executed by one
+ * whole warp; vt = virtual position of the tile start, a multiple of 32.  One atomic exchange
+ * per lane puts the position into the slot's head and returns its predecessor: lanes of one
+ * batch that share a slot are served in ascending lane (= position) order, so each receives the
+ * lane before it and the highest one stays in the head.  The last batch of a stream runs all 32
+ * lanes: the positions past the end sit in the gap before the next stream, where no query ever
+ * looks (a candidate is valid only up to the query's own position inside its stream). */
+template <int K>
+__device__ __forceinline__ void k1_build_level(uint32_t *heads, uint16_t *links, const uint32_t *W,
+                                               uint32_t vt, uint32_t tile_n)
+{
+    const uint32_t  lane = lane_id();
+    uint32_t       *hd = heads + (K - 2) * kK1Slots;
     uint16_t       *lk = links + (K - 2) * kK1LinkRing + lane;
     const uint32_t *Wl = W + lane;
     uint32_t        hnext = k1_hash_at<K>(Wl, vt & (kK1WRing - 1));
 #pragma unroll 1   /* eleven specialised copies of this loop run side by side: keep them small for the instruction cache */
     for (uint32_t b = 0; b < tile_n; b += 32) {
         const uint32_t vb = vt + b;                       /* warp-uniform, a multiple of 32 */
-        const uint32_t pos16 = (vb & 0xFFFFu) | lane;
+        const uint32_t pos = vb | lane;
         const uint32_t h = hnext;
-        uint16_t      *slot = hd + (h >> kSlotShift);
+        uint32_t      *slot = hd + (h >> kSlotShift);
         hnext = k1_hash_at<K>(Wl, (vb + 32) & (kK1WRing - 1));   /* next batch: independent of the table */
 
-        const uint32_t old = *slot;
-        __syncwarp();                        /* every lane has the pre-batch head       */
-        *slot = static_cast<uint16_t>(pos16);
-        __syncwarp();
-        const uint32_t back = *slot;
-        const bool     loser = back != pos16; /* another lane of this batch owns my slot */
-        uint32_t       dist = pos16 - old;    /* its low 16 bits are the distance        */
-        if (__any_sync(LZS_FULL_MASK, loser)) {
-            /* order the duplicated lanes only: the slot's winner (lane = back & 31) and its losers */
-            const uint32_t named = __reduce_or_sync(LZS_FULL_MASK, loser ? (1u << (back & 31u)) : 0u);
-            const bool     dup = loser || ((named >> lane) & 1u);
-            const uint32_t grp = __match_any_sync(LZS_FULL_MASK, dup ? (h >> kSlotShift) : 0xFFFFFFFFu);
-            if (dup) {
-                const uint32_t lower = grp & lt;
-                if (lower) dist = lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(lower))));
-                if ((grp >> lane) == 1u && loser) *slot = static_cast<uint16_t>(pos16);  /* last one owns the head */
-            }
-            __syncwarp();
-        }
-        uint32_t e = (h >> (kTagShift - 11)) & 0xF800u;   /* tag << 11 */
-        if ((dist & 0xF800u) == 0u) e |= dist & kLinkDistMask;   /* further than the window: no link */
+        uint32_t       old = smem_exch(slot, pos);
+        const uint32_t rel = old - vb;                    /* < 32: the position of a lane of this batch */
+        if (__any_sync(LZS_FULL_MASK, rel < 32u && rel > lane)) old = k1_relink(slot, h >> kSlotShift, old, vb, pos);
+        const uint32_t dist = pos - old;
+        uint32_t       e = (h >> (kTagShift - 11)) & 0xF800u;   /* tag << 11 */
+        if (dist <= kWindow) e |= dist;                   /* further than the window: no link */
         lk[vb & (kK1LinkRing - 1)] = static_cast<uint16_t>(e);
     }
 }
@@ -302,26 +324,56 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
     return (best << kMatchOffBits) | bd;
 }
 
+/* Queries of one tile, handed out in chunks of 32 positions (one per warp pass) from a counter in
+ * shared memory, so that a warp that drew cheap positions takes more of them. */
+__device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_chunk, const uint16_t *links,
+                                                const uint16_t *runs, const uint32_t *W, match_t *mout)
+{
+    const uint32_t lane = lane_id();
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(next_chunk, 1u);
+        c = __shfl_sync(LZS_FULL_MASK, c, 0);
+        const uint32_t r = c * 32u + lane;
+        if (c * 32u >= d.tile_n) break;
+        if (r < d.tile_n) {
+            const uint32_t i = d.t0 + r;
+            mout[i] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(kK1Threads, 1)
 k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          const uint32_t *__restrict__ in_len, match_t *__restrict__ matches, uint32_t n_streams,
          uint32_t *__restrict__ next_stream)
 {
     LZS_DYN_SMEM(uint8_t, smem);
-    uint16_t *heads = reinterpret_cast<uint16_t *>(smem);
-    uint16_t *links = heads + kK1Levels * kK1Slots;
+    uint32_t *heads = reinterpret_cast<uint32_t *>(smem);
+    uint16_t *links = reinterpret_cast<uint16_t *>(heads + kK1Levels * kK1Slots);
     uint16_t *runs = links + kK1Levels * kK1LinkRing;
     uint32_t *W = reinterpret_cast<uint32_t *>(runs + kK1LinkRing);
-    __shared__ K1Tile   s_desc[4];           /* tile g is described in s_desc[g & 3]             */
+    __shared__ K1Tile   s_desc[8];           /* tile g is described in s_desc[g & 7]             */
+    __shared__ uint64_t s_full[kK1Depth];    /* tile g built: one arrival per build thread, phase g / depth */
+    __shared__ uint64_t s_empty[kK1Depth];   /* tile g queried: one arrival per query thread              */
     __shared__ uint32_t s_filled;            /* tiles whose grams and descriptor are in place     */
-    __shared__ uint32_t s_qdone;             /* query-warp completions: tile q is done at 16(q+1) */
+    __shared__ uint32_t s_qdone[kK1Depth];   /* query-warp completions per stage: tile q is done at 16 (q / depth + 1) in [q % depth] */
+    __shared__ uint32_t s_qnext[16];         /* next chunk of tile g to query, in s_qnext[g & 15]  */
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31u;
 
-    for (uint32_t x = tid; x < kK1Levels * (kK1Slots + kK1LinkRing) + kK1LinkRing; x += kK1Threads) heads[x] = 0;
-    if (tid == 0) { s_filled = 0; s_qdone = 0; }
+    for (uint32_t x = tid; x < kK1Levels * kK1Slots; x += kK1Threads) heads[x] = 0;
+    for (uint32_t x = tid; x < (kK1Levels + 1) * kK1LinkRing; x += kK1Threads) links[x] = 0;
+    if (tid == 0) s_filled = 0;
+    if (tid < kK1Depth) s_qdone[tid] = 0;
+    if (tid < 16) s_qnext[tid] = 0;
+    if (tid < kK1Depth) {
+        mbar_init(&s_full[tid], kK1BuildThreads);
+        mbar_init(&s_empty[tid], kK1QueryThreads);
+    }
     __syncthreads();
 
     if (warp == static_cast<uint32_t>(kK1BuildWarps)) {
@@ -346,8 +398,11 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 /* byte shift of this lane's grams: the same for every step (steps are multiples of 32) */
                 const uint32_t sh = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(src) + lane +
                                                            ((t0 == 0) ? 0u : t0 + kK1Ahead)) & 3u) * 8u;
-                if (g >= 3) {
-                    while (*reinterpret_cast<volatile uint32_t *>(&s_qdone) < (g - 2u) * kK1QueryWarps) spin_pause();
+                if (g > kK1Depth) {          /* every query warp has left tile g - depth - 1 */
+                    const uint32_t q = g - kK1Depth - 1u;
+                    while (*reinterpret_cast<volatile uint32_t *>(&s_qdone[q & (kK1Depth - 1u)]) <
+                           (q / kK1Depth + 1u) * kK1QueryWarps)
+                        spin_pause();
                     __threadfence_block();
                 }
                 /* grams are kept kK1Ahead positions beyond the tile: 8 for the 12-byte compares plus
@@ -385,17 +440,21 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 if (lane == 0) {
                     K1Tile d;
                     d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0;
-                    s_desc[g & 3u] = d;
+                    s_desc[g & 7u] = d;
+                    s_qnext[g & 15u] = 0;    /* nobody can still be on tile g - 16 */
                 }
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_filled) = g + 1u;
             }
         }
-        if (g >= 3) {
-            while (*reinterpret_cast<volatile uint32_t *>(&s_qdone) < (g - 2u) * kK1QueryWarps) spin_pause();
+        if (g > kK1Depth) {
+            const uint32_t q = g - kK1Depth - 1u;
+            while (*reinterpret_cast<volatile uint32_t *>(&s_qdone[q & (kK1Depth - 1u)]) <
+                   (q / kK1Depth + 1u) * kK1QueryWarps)
+                spin_pause();
         }
-        if (lane == 0) s_desc[g & 3u].sid = kK1EndOfWork;
+        if (lane == 0) s_desc[g & 7u].sid = kK1EndOfWork;
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_filled) = g + 1u;
@@ -404,11 +463,12 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          * Independent of each other: a warp waits for the loader (flag), for the query group to
          * have left the tile two back (named barrier), builds, and signals the query group. */
         for (uint32_t g = 0;; g++) {
-            const uint32_t buf = g & 1u;
+            const uint32_t buf = g & (kK1Depth - 1u);
             while (*reinterpret_cast<volatile uint32_t *>(&s_filled) <= g) spin_pause();
             __threadfence_block();
-            const K1Tile d = s_desc[g & 3u];
-            if (g >= 2) named_sync(kBarEmpty0 + static_cast<int>(buf), kK1PipeThreads);
+            const K1Tile d = s_desc[g & 7u];
+            /* the query warps must have left the tile that used this stage before (tile g - depth) */
+            if (g >= kK1Depth) mbar_wait(&s_empty[buf], (g / kK1Depth - 1u) & 1u);
             if (d.sid != kK1EndOfWork) {
                 const uint32_t vt = d.v0 + d.t0;
                 switch (warp) {
@@ -426,25 +486,20 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     default: k1_build_runs(runs, W, d.v0, d.t0, d.tile_n); break;
                 }
             }
-            named_arrive(kBarFull0 + static_cast<int>(buf), kK1PipeThreads);
+            mbar_arrive(&s_full[buf]);
             if (d.sid == kK1EndOfWork) break;
         }
     } else {
         /* ================= query warps: one query per position ================= */
-        const uint32_t qtid = tid - 32u * (kK1BuildWarps + 1);
         for (uint32_t g = 0;; g++) {
-            const uint32_t buf = g & 1u;
-            named_sync(kBarFull0 + static_cast<int>(buf), kK1PipeThreads);
-            const K1Tile d = s_desc[g & 3u];
+            const uint32_t buf = g & (kK1Depth - 1u);
+            mbar_wait(&s_full[buf], (g / kK1Depth) & 1u);
+            const K1Tile d = s_desc[g & 7u];
             if (d.sid == kK1EndOfWork) break;
-            match_t *mout = matches + in_off[d.sid];
-            for (uint32_t r = qtid; r < d.tile_n; r += kK1QueryThreads) {
-                const uint32_t i = d.t0 + r;
-                mout[i] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
-            }
-            named_arrive(kBarEmpty0 + static_cast<int>(buf), kK1PipeThreads);
+            k1_query_chunks(d, &s_qnext[g & 15u], links, runs, W, matches + in_off[d.sid]);
+            mbar_arrive(&s_empty[buf]);
             __syncwarp();
-            if (lane == 0) atomicAdd(&s_qdone, 1u);      /* the loader may reuse the ring behind us */
+            if (lane == 0) atomicAdd(&s_qdone[buf], 1u);  /* the loader may reuse the ring behind us */
         }
     }
 }

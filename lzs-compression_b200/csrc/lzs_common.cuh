@@ -69,24 +69,52 @@ __device__ __forceinline__ void spin_pause()
 #endif
 }
 
-/* Named barriers (PTX bar.sync / bar.arrive): `count` threads take part in total;
- * sync waits for all of them, arrive only signals.  Used for producer/consumer
- * hand-off between warp groups of one CTA. */
-__device__ __forceinline__ void named_sync(int id, unsigned count)
+/* Shared-memory arrival barriers (PTX mbarrier): `count` arrivals complete a phase; any number
+ * of threads may wait for a phase without being counted, so producers and consumers of a
+ * hand-off never have to meet among themselves.  arrive has release, wait has acquire semantics
+ * at CTA scope.  Phases are used strictly in turn (a phase cannot complete twice before every
+ * waiter of the previous one has seen it -- the protocol of the caller guarantees that), so a
+ * waiter only needs the parity of the phase it waits for. */
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
 #ifdef LZS_SIMT_EMU
-    simt_named_barrier_sync(id, count);
+    *bar = (static_cast<uint64_t>(count) << 32) | count;      /* [63] phase, [62:32] count, [31:0] pending */
 #else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))),
+                 "r"(count)
+                 : "memory");
 #endif
 }
-__device__ __forceinline__ void named_arrive(int id, unsigned count)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
 #ifdef LZS_SIMT_EMU
-    simt_named_barrier_arrive(id, count);
+    uint64_t v = *bar;
+    uint32_t pending = static_cast<uint32_t>(v) - 1u;
+    if (pending == 0u) {
+        v ^= 1ull << 63;
+        pending = static_cast<uint32_t>(v >> 32) & 0x7FFFFFFFu;
+    }
+    *bar = (v & 0xFFFFFFFF00000000ull) | pending;
 #else
-    __threadfence_block();
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+#ifdef LZS_SIMT_EMU
+    while (static_cast<uint32_t>(*reinterpret_cast<volatile uint64_t *>(bar) >> 63) == (parity & 1u)) simt_yield();
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LZS_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LZS_MBAR_DONE;\n\t"
+        "bra LZS_MBAR_WAIT;\n\t"
+        "LZS_MBAR_DONE:\n\t}" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))),
+        "r"(parity & 1u)
+        : "memory");
 #endif
 }
 
