@@ -67,7 +67,8 @@ int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, 
 
 /* Individual stages of the compressor, for tests and profiling:
  * K1 writes one record per input byte, (len << 11) | offset with len 0 or 2..12;
- * K2+K3 turn records + input into streams. */
+ * K2+K3 turn records + input into streams.  `counter` is device scratch of at least 16 bytes
+ * (work counters and a status word, cleared by the call). */
 int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                                 uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream);
 int lzs_b200_parse_pack_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,

@@ -71,10 +71,14 @@ constexpr uint32_t kK1WMirror = 64;         /* the first grams again behind the 
 #ifndef LZS_K1_TILE
 #define LZS_K1_TILE 448
 #endif
+#ifndef LZS_K1_BUILD_UNROLL
+#define LZS_K1_BUILD_UNROLL 1
+#endif
 #ifndef LZS_K1_DEPTH
 #define LZS_K1_DEPTH 4
 #endif
 constexpr uint32_t kK1Tile = LZS_K1_TILE;   /* a multiple of 32; 448 = 14 batches  */
+constexpr int      kK1BuildUnroll = LZS_K1_BUILD_UNROLL;
 constexpr uint32_t kK1Depth = LZS_K1_DEPTH; /* tiles the build warps may be ahead of the query group (power of two) */
 /* Virtual positions between streams: 12 zero grams behind the last byte, then up to the next
  * multiple of 32 (every stream starts on a batch boundary, so a batch never straddles a ring
@@ -105,25 +109,16 @@ struct K1Tile {
     uint32_t sid, t0, tile_n, n, v0;
 };
 
-/* mask selecting the low `bytes` bytes of a little-endian word, bytes in 1..4 */
-__device__ __forceinline__ constexpr uint32_t low_bytes_mask(int bytes)
+/* Hash of the k-gram that starts the 12 bytes (w0, w1, w2); (m0, m1, m2) mask the bytes that
+ * belong to the gram.  Bits 31..21 are the table slot, bits 19..15 a 5-bit tag kept beside every
+ * chain link so that a query can reject most foreign entries of its slot without touching their
+ * bytes.  The three products are independent (one dependent multiply less than a chained hash).
+ * The masks are run-time values on purpose: all eleven level warps execute the SAME loop code,
+ * which is what keeps it resident in the instruction cache. */
+__device__ __forceinline__ uint32_t gram_hash(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t m0, uint32_t m1,
+                                              uint32_t m2)
 {
-    return bytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * bytes)) - 1u);
-}
-
-/* Hash of the K-gram that starts the 12 bytes (w0, w1, w2): bits 31..20 are the table
- * slot, bits 19..15 a 5-bit tag kept beside every chain link so that a query can
- * reject most foreign entries of its slot without touching their bytes.  The three
- * products are independent (one dependent multiply less than a chained hash). */
-template <int K>
-__device__ __forceinline__ uint32_t gram_hash_c(uint32_t w0, uint32_t w1, uint32_t w2)
-{
-    constexpr uint32_t m0 = low_bytes_mask(K >= 4 ? 4 : K);
-    constexpr uint32_t m1 = K <= 4 ? 0u : low_bytes_mask(K >= 8 ? 4 : K - 4);
-    constexpr uint32_t m2 = K <= 8 ? 0u : low_bytes_mask(K >= 12 ? 4 : K - 8);
-    uint32_t h = (w0 & m0) * 0x9E3779B1u;
-    if (K > 4) h ^= (w1 & m1) * 0x85EBCA77u;
-    if (K > 8) h ^= (w2 & m2) * 0xC2B2AE3Du;
+    uint32_t h = ((w0 & m0) * 0x9E3779B1u) ^ ((w1 & m1) * 0x85EBCA77u) ^ ((w2 & m2) * 0xC2B2AE3Du);
     h ^= h >> 15;
     h *= 0x27D4EB2Fu;
     return h;
@@ -144,18 +139,11 @@ __device__ __forceinline__ uint32_t lcp12(uint32_t a0, uint32_t a1, uint32_t a2,
     return base + (static_cast<uint32_t>(__ffs(static_cast<int>(x)) - 1) >> 3);
 }
 
-/* hash of the K-gram at gram-ring index x (x < kK1WRing; the mirror covers x + 8) */
-template <int K>
-__device__ __forceinline__ uint32_t k1_hash_at(const uint32_t *W, uint32_t x)
-{
-    return gram_hash_c<K>(W[x], K > 4 ? W[x + 4] : 0u, K > 8 ? W[x + 8] : 0u);
-}
-
-/* Exchange on a shared-memory word: returns the previous value. */
+/* Exchange on a shared-memory word: returns the previous value.  Called by all 32 lanes together. */
 __device__ __forceinline__ uint32_t smem_exch(uint32_t *p, uint32_t v)
 {
 #ifdef LZS_SIMT_EMU
-    return atomicExch(p, v);
+    return simt_warp_exch(p, v);
 #else
     uint32_t o;
     asm volatile("atom.shared.exch.b32 %0, [%1], %2;"
@@ -188,34 +176,44 @@ __device__ __noinline__ uint32_t k1_relink(uint32_t *slot, uint32_t key, uint32_
  * whole warp; vt = virtual position of the tile start, a multiple of 32.  One atomic exchange
  * per lane puts the position into the slot's head and returns its predecessor: lanes of one
  * batch that share a slot are served in ascending lane (= position) order, so each receives the
- * lane before it and the highest one stays in the head.  The last batch of a stream runs all 32
+ * lane before it and the highest one stays in the head.  That order is what sm_100a does
+ * (tools/micro/atoms_exch.cu), not something PTX promises, so the fast kernel only RECORDS whether
+ * a lane ever received a higher lane of its own batch (the returned flag; nothing in the loop
+ * waits for it) and the safe kernel (kSafe: every batch repaired with k1_relink, exact for any
+ * service order) re-does the whole batch of streams if that was ever seen.  The last batch of a stream runs all 32
  * lanes: the positions past the end sit in the gap before the next stream, where no query ever
  * looks (a candidate is valid only up to the query's own position inside its stream). */
-template <int K>
-__device__ __forceinline__ void k1_build_level(uint32_t *heads, uint16_t *links, const uint32_t *W,
-                                               uint32_t vt, uint32_t tile_n)
+template <bool kSafe>
+__device__ __forceinline__ uint32_t k1_build_level(uint32_t *hd, uint16_t *lk, const uint32_t *W, uint32_t vt,
+                                                   uint32_t tile_n, uint32_t m0, uint32_t m1, uint32_t m2)
 {
     const uint32_t  lane = lane_id();
-    uint32_t       *hd = heads + (K - 2) * kK1Slots;
-    uint16_t       *lk = links + (K - 2) * kK1LinkRing + lane;
     const uint32_t *Wl = W + lane;
-    uint32_t        hnext = k1_hash_at<K>(Wl, vt & (kK1WRing - 1));
-#pragma unroll 1   /* eleven specialised copies of this loop run side by side: keep them small for the instruction cache */
+    lk += lane;
+    uint32_t x = vt & (kK1WRing - 1);
+    uint32_t hnext = gram_hash(Wl[x], Wl[x + 4], Wl[x + 8], m0, m1, m2);
+    uint32_t disorder = 0;
+#pragma unroll kK1BuildUnroll   /* one copy serves all eleven levels */
     for (uint32_t b = 0; b < tile_n; b += 32) {
         const uint32_t vb = vt + b;                       /* warp-uniform, a multiple of 32 */
         const uint32_t pos = vb | lane;
         const uint32_t h = hnext;
         uint32_t      *slot = hd + (h >> kSlotShift);
-        hnext = k1_hash_at<K>(Wl, (vb + 32) & (kK1WRing - 1));   /* next batch: independent of the table */
+        x = (vb + 32) & (kK1WRing - 1);
+        hnext = gram_hash(Wl[x], Wl[x + 4], Wl[x + 8], m0, m1, m2);   /* next batch: independent of the table */
 
         uint32_t       old = smem_exch(slot, pos);
-        const uint32_t rel = old - vb;                    /* < 32: the position of a lane of this batch */
-        if (__any_sync(LZS_FULL_MASK, rel < 32u && rel > lane)) old = k1_relink(slot, h >> kSlotShift, old, vb, pos);
+        __syncwarp();                                     /* batch after batch, also formally */
+        if (kSafe)
+            old = k1_relink(slot, h >> kSlotShift, old, vb, pos);
+        else
+            disorder |= (pos - old) >> 31;                /* received a LATER position: not the order assumed */
         const uint32_t dist = pos - old;
         uint32_t       e = (h >> (kTagShift - 11)) & 0xF800u;   /* tag << 11 */
         if (dist <= kWindow) e |= dist;                   /* further than the window: no link */
         lk[vb & (kK1LinkRing - 1)] = static_cast<uint16_t>(e);
     }
+    return disorder;
 }
 
 /* Run table of one tile (one whole warp).  For every position p it records how far back
@@ -344,11 +342,17 @@ __device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_
     }
 }
 
+/* ctl[0]: stream counter of the fast launch, ctl[1]: of the safe launch, ctl[2]: set by the fast
+ * launch when an exchange order was observed that the fast insert does not handle.  The safe
+ * launch follows the fast one on the same stream and returns at once unless ctl[2] is set. */
+template <bool kSafe>
 __global__ void __launch_bounds__(kK1Threads, 1)
 k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          const uint32_t *__restrict__ in_len, match_t *__restrict__ matches, uint32_t n_streams,
-         uint32_t *__restrict__ next_stream)
+         uint32_t *__restrict__ ctl)
 {
+    if (kSafe && *reinterpret_cast<volatile uint32_t *>(ctl + 2) == 0u) return;
+    uint32_t *next_stream = ctl + (kSafe ? 1 : 0);
     LZS_DYN_SMEM(uint8_t, smem);
     uint32_t *heads = reinterpret_cast<uint32_t *>(smem);
     uint16_t *links = reinterpret_cast<uint16_t *>(heads + kK1Levels * kK1Slots);
@@ -462,6 +466,12 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
         /* ================= build warps: one level each (the twelfth: the run table) =================
          * Independent of each other: a warp waits for the loader (flag), for the query group to
          * have left the tile two back (named barrier), builds, and signals the query group. */
+        /* byte masks of this warp's gram length k = warp + 2 */
+        const uint32_t k = warp + 2u;
+        const uint32_t m0 = k >= 4u ? 0xFFFFFFFFu : ((1u << (8u * k)) - 1u);
+        const uint32_t m1 = k >= 8u ? 0xFFFFFFFFu : (k <= 4u ? 0u : ((1u << (8u * (k - 4u))) - 1u));
+        const uint32_t m2 = k >= 12u ? 0xFFFFFFFFu : (k <= 8u ? 0u : ((1u << (8u * (k - 8u))) - 1u));
+        uint32_t disorder = 0;
         for (uint32_t g = 0;; g++) {
             const uint32_t buf = g & (kK1Depth - 1u);
             while (*reinterpret_cast<volatile uint32_t *>(&s_filled) <= g) spin_pause();
@@ -471,24 +481,16 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             if (g >= kK1Depth) mbar_wait(&s_empty[buf], (g / kK1Depth - 1u) & 1u);
             if (d.sid != kK1EndOfWork) {
                 const uint32_t vt = d.v0 + d.t0;
-                switch (warp) {
-                    case 0:  k1_build_level<2>(heads, links, W, vt, d.tile_n); break;
-                    case 1:  k1_build_level<3>(heads, links, W, vt, d.tile_n); break;
-                    case 2:  k1_build_level<4>(heads, links, W, vt, d.tile_n); break;
-                    case 3:  k1_build_level<5>(heads, links, W, vt, d.tile_n); break;
-                    case 4:  k1_build_level<6>(heads, links, W, vt, d.tile_n); break;
-                    case 5:  k1_build_level<7>(heads, links, W, vt, d.tile_n); break;
-                    case 6:  k1_build_level<8>(heads, links, W, vt, d.tile_n); break;
-                    case 7:  k1_build_level<9>(heads, links, W, vt, d.tile_n); break;
-                    case 8:  k1_build_level<10>(heads, links, W, vt, d.tile_n); break;
-                    case 9:  k1_build_level<11>(heads, links, W, vt, d.tile_n); break;
-                    case 10: k1_build_level<12>(heads, links, W, vt, d.tile_n); break;
-                    default: k1_build_runs(runs, W, d.v0, d.t0, d.tile_n); break;
-                }
+                if (warp < static_cast<uint32_t>(kK1Levels))
+                    disorder |= k1_build_level<kSafe>(heads + warp * kK1Slots, links + warp * kK1LinkRing, W, vt,
+                                                      d.tile_n, m0, m1, m2);
+                else
+                    k1_build_runs(runs, W, d.v0, d.t0, d.tile_n);
             }
             mbar_arrive(&s_full[buf]);
             if (d.sid == kK1EndOfWork) break;
         }
+        if (!kSafe && __any_sync(LZS_FULL_MASK, disorder != 0u) && lane == 0) atomicOr(ctl + 2, 1u);
     } else {
         /* ================= query warps: one query per position ================= */
         for (uint32_t g = 0;; g++) {

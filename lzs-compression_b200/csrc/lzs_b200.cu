@@ -66,7 +66,9 @@ int device_info(DeviceInfo **out)
     DeviceInfo &d = info[dev];
     if (!d.ok) {
         CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
-        CUDA_TRY(cudaFuncSetAttribute(lzs::k1_match, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(lzs::k1_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(lzs::kK1SmemBytes)));
+        CUDA_TRY(cudaFuncSetAttribute(lzs::k1_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lzs::kK1SmemBytes)));
         CUDA_TRY(cudaFuncSetAttribute(lzs::k4_decode<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(lzs::k4_smem_bytes<4>())));
@@ -164,11 +166,15 @@ int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const
     int         rc = device_info(&d);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), st));
     const unsigned grid = n_streams < static_cast<uint32_t>(d->sms) ? n_streams : static_cast<unsigned>(d->sms);
-    lzs::k1_match<<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
-                                                                   counter);
-    g_launches++;
+    lzs::k1_match<false><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
+                                                                          counter);
+    /* the exact-for-any-hardware variant: returns at once unless the fast launch saw an exchange
+     * order it does not handle (never on sm_100a); on the stream, so nothing waits on the host */
+    lzs::k1_match<true><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
+                                                                         counter);
+    g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return LZS_B200_OK;
 }

@@ -88,10 +88,20 @@ def decode(streams, caps, lanes=8, grid=2, align=16, lead=0, out_lead=0):
     return _collect(dst, out_off, caps, out_len, "decoder")
 
 
+last_match_disorder = 0   # what the fast K1 launch recorded in the last match() (1: the safe launch ran)
+
+
+def scramble_exchanges(on):
+    """Serve the lanes of shared-memory atomic exchanges in a scrambled order (test knob)."""
+    lib().emu_scramble_exchanges(1 if on else 0)
+
+
 def match(streams, grid=1, align=16, lead=0):
+    global last_match_disorder
     src, in_off, in_len = pack_streams(streams, align, lead)
     m = np.zeros(len(src) + 16, dtype=np.uint16)
-    lib().emu_match(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p), len(streams), grid)
+    last_match_disorder = lib().emu_match(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p),
+                                          len(streams), grid)
     return [m[int(o):int(o) + int(l)].copy() for o, l in zip(in_off, in_len)], (src, in_off, in_len, m)
 
 

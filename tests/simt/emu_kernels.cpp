@@ -37,12 +37,21 @@ extern "C" int emu_decode(const uint8_t *in, const uint64_t *in_off, const uint3
 extern "C" int emu_match(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                          uint16_t *matches, uint32_t n, unsigned grid)
 {
-    uint32_t counter = 0;
+    /* as the host does: the fast launch, then the safe launch (which returns at once unless the
+     * fast one recorded an exchange order it does not handle).  Returns that record. */
+    uint32_t ctl[4] = {0, 0, 0, 0};
     simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
-        lzs::k1_match(in, in_off, in_len, matches, n, &counter);
+        lzs::k1_match<false>(in, in_off, in_len, matches, n, ctl);
     });
-    return 0;
+    simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
+        lzs::k1_match<true>(in, in_off, in_len, matches, n, ctl);
+    });
+    return static_cast<int>(ctl[2]);
 }
+
+/* Test knob: serve the lanes of an atomic exchange in a scrambled order (real hardware serves
+ * them in ascending lane order; the product must be exact either way). */
+extern "C" void emu_scramble_exchanges(int on) { simt::g_scramble_exchanges = on; }
 
 extern "C" int emu_parse_pack(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                               const uint16_t *matches, uint8_t *out, const uint64_t *out_off,

@@ -87,3 +87,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
 }
 
 }  // namespace simt
+
+namespace simt {
+int g_scramble_exchanges = 0;
+}  // namespace simt

@@ -104,6 +104,28 @@ def test_compress_streams_share_tables_safely():
     assert emu.compress(data, grid=1) == [o.compress(d) for d in data]
 
 
+def test_match_finder_exact_for_any_exchange_order(cases):
+    """K1's fast insert relies on sm_100a serving the lanes of a shared-memory exchange in ascending
+    lane order.  With the emulator serving them in a scrambled order the fast launch must notice,
+    and the safe launch that follows must produce the exact records anyway."""
+    data = [helpers.corpus(helpers.CORPUS_BINARY, 1, 3000, first_index=2).tobytes(),
+            helpers.corpus(helpers.CORPUS_TEXT, 1, 2500, first_index=3).tobytes(), b"\0" * 700, cases["run_a_5000"]
+            if "run_a_5000" in cases else b"a" * 5000]
+    want = [_want_matches(d) for d in data]
+    got, _ = emu.match(data)
+    assert emu.last_match_disorder == 0, "in-order exchanges must not trigger the safe launch"
+    for w, g in zip(want, got):
+        assert (w == g).all()
+    emu.scramble_exchanges(True)
+    try:
+        got, _ = emu.match(data)
+        assert emu.last_match_disorder == 1, "the scrambled order went unnoticed"
+    finally:
+        emu.scramble_exchanges(False)
+    for w, g in zip(want, got):
+        assert (w == g).all()
+
+
 def test_compress_64k_chunk_crosses_16bit_positions():
     o = helpers.oracle()
     d = helpers.corpus(helpers.CORPUS_MIXED, 1, 70000, first_index=1).tobytes()
