@@ -72,7 +72,7 @@ constexpr uint32_t kK1WMirror = 64;         /* the first grams again behind the 
 #define LZS_K1_TILE 448
 #endif
 #ifndef LZS_K1_BUILD_UNROLL
-#define LZS_K1_BUILD_UNROLL 1
+#define LZS_K1_BUILD_UNROLL 2
 #endif
 #ifndef LZS_K1_DEPTH
 #define LZS_K1_DEPTH 4
@@ -90,7 +90,6 @@ constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the 
 #endif
 constexpr int      kK1QueryWarps = LZS_K1_QW;
 constexpr int      kK1Threads = 32 * (kK1BuildWarps + 1 + kK1QueryWarps);   /* + the loader warp */
-constexpr int      kK1LoadUnroll = 8;       /* global loads in flight per loader lane */
 constexpr unsigned kK1BuildThreads = 32 * kK1BuildWarps;
 constexpr unsigned kK1QueryThreads = 32 * kK1QueryWarps;
 constexpr size_t   kK1SmemBytes = static_cast<size_t>(kK1Levels) * kK1Slots * 4 +
@@ -322,6 +321,55 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
     return (best << kMatchOffBits) | bd;
 }
 
+/* The loader's view of one tile: the aligned words that cover the tile's new grams.  Lane l holds
+ * words l, l + 32, ... of the range that starts at the aligned word containing byte p_lo of the
+ * stream (one more 32-word row than there are 128-position groups, because a gram reaches into
+ * the following word).  Addresses beyond the stream's last word are clamped and read as zero. */
+constexpr int kK1LoadGroups = static_cast<int>((kK1Tile + kK1Ahead + 127) / 128);
+struct K1Words {
+    uint32_t w[kK1LoadGroups + 1];
+};
+__device__ __forceinline__ void k1_load_words(K1Words &r, const uint8_t *src, uint32_t p_lo, uintptr_t wlast)
+{
+    const uintptr_t base = (reinterpret_cast<uintptr_t>(src) + p_lo) & ~static_cast<uintptr_t>(3);
+#pragma unroll
+    for (int k = 0; k <= kK1LoadGroups; k++) {
+        const uintptr_t a = base + 4u * (static_cast<uint32_t>(k) * 32u + lane_id());
+        const uint32_t  v = __ldg(reinterpret_cast<const uint32_t *>(a <= wlast ? a : wlast));
+        r.w[k] = (a <= wlast) ? v : 0u;
+    }
+}
+/* grams p_lo .. p_hi-1 of the stream from the words loaded above: lane l makes the four grams
+ * 4l .. 4l+3 of every 128-position group out of words l, l+1, l+2 */
+__device__ __forceinline__ void k1_store_grams(const K1Words &r, uint32_t *W, const uint8_t *src, uint32_t v0,
+                                               uint32_t p_lo, uint32_t p_hi, uint32_t n)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t m = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(src) + p_lo) & 3u);   /* warp-uniform */
+#pragma unroll
+    for (int k = 0; k < kK1LoadGroups; k++) {
+        const uint32_t x0 = r.w[k];
+        const uint32_t d1 = __shfl_down_sync(LZS_FULL_MASK, r.w[k], 1), n1 = __shfl_sync(LZS_FULL_MASK, r.w[k + 1], 0);
+        const uint32_t d2 = __shfl_down_sync(LZS_FULL_MASK, r.w[k], 2),
+                       n2 = __shfl_sync(LZS_FULL_MASK, r.w[k + 1], (lane + 2u) & 31u);
+        const uint32_t x1 = lane == 31u ? n1 : d1;
+        const uint32_t x2 = lane >= 30u ? n2 : d2;
+        const uint32_t q0 = p_lo + static_cast<uint32_t>(k) * 128u + 4u * lane;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t o = m + j;                     /* byte offset from word l: 0..6 */
+            const uint32_t g = __funnelshift_r(o < 4u ? x0 : x1, o < 4u ? x1 : x2, (o & 3u) * 8u);
+            const uint32_t q = q0 + j;
+            if (q < p_hi) {
+                const uint32_t x = (v0 + q) & (kK1WRing - 1);
+                const uint32_t w = (q < n) ? g : 0u;
+                W[x] = w;
+                if (x < kK1WMirror) W[kK1WRing + x] = w;
+            }
+        }
+    }
+}
+
 /* Queries of one tile, handed out in chunks of 32 positions (one per warp pass) from a counter in
  * shared memory, so that a warp that drew cheap positions takes more of them. */
 __device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_chunk, const uint16_t *links,
@@ -398,10 +446,18 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             const uintptr_t wlast = (reinterpret_cast<uintptr_t>(src) + (n ? n - 1u : 0u)) & ~static_cast<uintptr_t>(3);
             const uint32_t v0 = vnext;
             vnext = (v0 + n + 16u + 31u) & ~31u;
+            if (n == 0) continue;            /* nothing to match, and no word of it may be touched */
+            /* grams are kept kK1Ahead positions beyond the tile: 8 for the 12-byte compares plus the
+             * 32 positions whose hashes the build warps prefetch in their last batch.  The words of
+             * the NEXT tile are requested before this tile's grams are written, so the DRAM latency
+             * is paid once per stream, not once per tile. */
+            K1Words cur;
+            k1_load_words(cur, src, 0u, wlast);
             for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
-                /* byte shift of this lane's grams: the same for every step (steps are multiples of 32) */
-                const uint32_t sh = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(src) + lane +
-                                                           ((t0 == 0) ? 0u : t0 + kK1Ahead)) & 3u) * 8u;
+                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + kK1Ahead;
+                const uint32_t p_hi = umin32(t0 + kK1Tile + kK1Ahead, n + 12u);
+                K1Words nxt;
+                k1_load_words(nxt, src, t0 + kK1Tile + kK1Ahead, wlast);
                 if (g > kK1Depth) {          /* every query warp has left tile g - depth - 1 */
                     const uint32_t q = g - kK1Depth - 1u;
                     while (*reinterpret_cast<volatile uint32_t *>(&s_qdone[q & (kK1Depth - 1u)]) <
@@ -409,38 +465,8 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         spin_pause();
                     __threadfence_block();
                 }
-                /* grams are kept kK1Ahead positions beyond the tile: 8 for the 12-byte compares plus
-                 * the 32 positions whose hashes the build warps prefetch in their last batch */
-                const uint32_t p_lo = (t0 == 0) ? 0u : t0 + kK1Ahead;
-                const uint32_t p_hi = umin32(t0 + kK1Tile + kK1Ahead, n + 12u);
-                for (uint32_t pb = p_lo; pb < p_hi; pb += 32u * kK1LoadUnroll) {
-                    /* branch-free (addresses clamped to the stream's last aligned word), so that
-                     * all the loads of a step are in flight together */
-                    uint32_t lo[kK1LoadUnroll], hi[kK1LoadUnroll], w[kK1LoadUnroll];
-#pragma unroll
-                    for (int j = 0; j < kK1LoadUnroll; j++) {
-                        const uint32_t  q = pb + static_cast<uint32_t>(j) * 32u + lane;
-                        const uintptr_t a = (reinterpret_cast<uintptr_t>(src) + q) & ~static_cast<uintptr_t>(3);
-                        lo[j] = __ldg(reinterpret_cast<const uint32_t *>(a < wlast ? a : wlast));
-                        hi[j] = __ldg(reinterpret_cast<const uint32_t *>(a + 4 < wlast ? a + 4 : wlast));
-                    }
-#pragma unroll
-                    for (int j = 0; j < kK1LoadUnroll; j++) {
-                        const uint32_t  q = pb + static_cast<uint32_t>(j) * 32u + lane;
-                        const uintptr_t a = (reinterpret_cast<uintptr_t>(src) + q) & ~static_cast<uintptr_t>(3);
-                        const uint32_t  h = (a + 4 <= wlast) ? hi[j] : 0u;     /* word beyond the stream: zero */
-                        w[j] = (q < n) ? __funnelshift_r(lo[j], h, sh) : 0u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < kK1LoadUnroll; j++) {
-                        const uint32_t q = pb + static_cast<uint32_t>(j) * 32u + lane;
-                        if (q < p_hi) {
-                            const uint32_t x = (v0 + q) & (kK1WRing - 1);
-                            W[x] = w[j];
-                            if (x < kK1WMirror) W[kK1WRing + x] = w[j];
-                        }
-                    }
-                }
+                k1_store_grams(cur, W, src, v0, p_lo, p_hi, n);
+                cur = nxt;
                 if (lane == 0) {
                     K1Tile d;
                     d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0;
