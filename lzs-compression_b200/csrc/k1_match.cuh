@@ -19,16 +19,14 @@
  *   exactly the reference's strict '>' / nearest-first tie-break).
  *
  *   P_k is "previous equal element" over the sequence of k-grams.  One warp per
- *   level k keeps a 4096-slot last-occurrence table in shared memory and inserts
- *   positions in order, 32 at a time.  Every lane reads the old head of its slot,
- *   all lanes store their position, and a read-back tells a lane whether another
- *   lane of the same batch shares its slot; only then are the few duplicated
- *   lanes ordered with MATCH.ANY (whose cost on sm_100a grows with the number of
- *   distinct keys: ~12 cycles each, so it is never run on 32 distinct slots).
+ *   level k keeps a 2048-slot last-occurrence table (32-bit heads) in shared memory
+ *   and inserts positions in order, 32 at a time: one atomic exchange per lane puts
+ *   the position into its slot and returns the predecessor (see k1_build_level for
+ *   why that is exact, and for the safe launch that backs the assumption it makes).
  *   Each position stores the distance to its predecessor in the same SLOT; slots
  *   are hashes, so a query verifies bytes and, on a foreign entry, follows the
  *   distance chain (every in-window position of the slot is on it, nearest
- *   first).  Table and chain garbage (stale entries, 16-bit aliasing) can only
+ *   first).  Table and chain garbage (stale entries, aliasing) can only
  *   produce candidates that fail the byte check, never a wrong answer -- the same
  *   argument that lets the reference run on uninitialised tables
  *   (lzs-compression.c:253-254).
@@ -39,19 +37,23 @@
  *   without a candidate ends the search.
  *
  * Layout: one persistent CTA per SM (216 KiB of shared memory: 11 head tables,
- * 11 link rings, the run table, a ring of 4-byte grams), streams pulled from a global counter and
- * walked in 992-position tiles.  The CTA is warp specialised: 12 build warps (one
- * per level plus the run table) run one tile ahead of 16 query warps; the two groups hand tiles over
- * through named barriers (double buffered).  Positions are numbered continuously
- * across the streams a CTA processes ("virtual positions"), so the rings need no
- * clearing between streams; a candidate is valid only if its distance does not
- * exceed the position inside the current stream.
+ * 11 link rings, the run table, a ring of 4-byte grams), 29 warps in four roles:
+ *   - 1 loader warp pulls streams from a global counter, cuts them into 448-position
+ *     tiles and fills the gram ring (aligned word loads, a tile ahead; shuffles and
+ *     funnel shifts make the grams), publishing each tile by a flag;
+ *   - 11 level warps + 1 run-table warp build a tile each at their own pace;
+ *   - 16 query warps take the tile's positions in chunks of 32 from a counter.
+ * Tiles are handed from the build warps to the query warps and back through
+ * mbarriers (arrive / wait-on-phase), four tiles deep, so no warp ever has to meet
+ * the other warps of its own group: a level warp only waits for "the query warps
+ * have left the tile that used this stage before", a query warp only for "all
+ * twelve build warps have finished this tile".  Positions are numbered
+ * continuously across the streams a CTA processes ("virtual positions", every
+ * stream starting on a multiple of 32), so the rings need no clearing between
+ * streams; a candidate is valid only if its distance does not exceed the position
+ * inside the current stream.
  *
- * Tried and measured slower on B200 (see profiles/README.md): several levels per build
- * warp (fewer instructions, but one warp's dependent-issue latency then bounds a batch),
- * and a software-pipelined insert that takes the read-back off the critical path
- * (lanes in reverse position order, because sm_100a lets the LOWEST lane win a
- * shared-memory store conflict -- tools/micro/sts_winner.cu).
+ * What was tried and what it measured: profiles/k1_experiments.md.
  *
  * Output: one uint16 per input byte, (len << 11) | offset, consumed by K2.
  * HBM traffic per input byte: 1 B read + 2 B written (intermediate).
@@ -430,9 +432,9 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
 
     if (warp == static_cast<uint32_t>(kK1BuildWarps)) {
         /* ================= loader: streams -> tiles, 4-byte grams into the ring =================
-         * Runs ahead of the build warps (up to three tiles ahead of the query group, which is what
-         * the gram ring holds), so the global-load latency is off everybody's critical path and
-         * the build warps never have to meet each other. */
+         * Runs ahead of the build warps (up to depth + 1 tiles ahead of the slowest query warp,
+         * which is what the gram ring holds), so the global-load latency is off everybody's
+         * critical path and the build warps never have to meet each other. */
         uint32_t g = 0;                      /* tiles described so far                  */
         uint32_t vnext = 4096;               /* virtual position of the next stream     */
         for (;;) {
@@ -490,8 +492,9 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
         if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_filled) = g + 1u;
     } else if (warp < static_cast<uint32_t>(kK1BuildWarps)) {
         /* ================= build warps: one level each (the twelfth: the run table) =================
-         * Independent of each other: a warp waits for the loader (flag), for the query group to
-         * have left the tile two back (named barrier), builds, and signals the query group. */
+         * Independent of each other: a warp waits for the loader (flag) and for the query warps to
+         * have left the tile that used this stage before (mbarrier phase), builds, and arrives on
+         * the stage's "built" mbarrier. */
         /* byte masks of this warp's gram length k = warp + 2 */
         const uint32_t k = warp + 2u;
         const uint32_t m0 = k >= 4u ? 0xFFFFFFFFu : ((1u << (8u * k)) - 1u);

@@ -1,0 +1,19 @@
+#!/bin/sh
+# Everything profiles/ is made from, in one GPU-box call (run from the repo root under gpurun):
+#   tests, both bench arms, the ncu launch list of the bench, one full ncu capture per kernel,
+#   the packets / chunk-size sweep.  Outputs land in gpurun_out/.
+R=${1:-r1}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_gpu_tests.log 2>&1; tail -2 gpurun_out/${R}_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py --impl reference > gpurun_out/${R}_bench_reference.json 2> gpurun_out/${R}_bench_reference.err
+timeout 600 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
+cat gpurun_out/${R}_bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-e2e > gpurun_out/${R}_bench_under_ncu.log 2>&1
+for k in k1_match k23_parse_pack k4_decode; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/${R}_$k \
+      python tools/prof.py --mib 1024 --kind mixed --iters 1 > /dev/null 2>&1
+done
+timeout 900 python tools/sweep.py > gpurun_out/${R}_sweep.jsonl 2> gpurun_out/${R}_sweep.err; tail -3 gpurun_out/${R}_sweep.jsonl
+ls -la gpurun_out | tail -12
