@@ -37,3 +37,14 @@ def dec_call():
 print("compress_batch_host: %.1f ms" % t(comp_call))
 print("decompress_batch_host: %.1f ms" % t(dec_call))
 assert torch.equal(dec[:total], raw[:total])
+out_off = np.zeros(n, dtype=np.uint64); used = ctypes.c_uint64(0)
+def packed_call():
+    B.check(L.lzs_b200_compress_packed_host(p(raw), B._p(in_off, B.u64p), B._p(in_len, B.u32p), total, p(comp), n * stride, B._p(out_off, B.u64p), B._p(c_len, B.u32p), n, ctypes.cast(ctypes.byref(used), B.u64p)))
+try:
+    print("compress_packed_host: %.1f ms" % t(packed_call))
+    def dec_packed():
+        B.check(L.lzs_b200_decompress_batch_host(p(comp), B._p(out_off, B.u64p), B._p(c_len, B.u32p), used.value, p(dec), B._p(in_off, B.u64p), B._p(in_len, B.u32p), B._p(d_len, B.u32p), total, n))
+    print("decompress_batch_host (packed input): %.1f ms" % t(dec_packed))
+    assert torch.equal(dec[:total], raw[:total])
+except Exception as e:
+    print("packed probe failed:", e)
