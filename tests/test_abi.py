@@ -69,6 +69,23 @@ def test_no_cpu_fallback_without_a_device(B):
     assert b"no CUDA device" in L.lzs_b200_last_error() or b"failed" in L.lzs_b200_last_error()
     assert B.lzs_compress(b"hello hello hello") == b""              # 0 bytes + stderr diagnostic
     assert B.lzs_decompress(bytes([0xC0, 0x00]), 16) == b""
+    # the file CLI over the same library: fails, writes nothing
+    cli = os.path.join(helpers.ROOT, "lzs-compression_b200", "bin", "lzs-b200")
+    if os.path.exists(cli):
+        src, dst = tmp_file("cli_in.bin", b"hello hello hello"), tmp_file("cli_out.lzs", None)
+        r = subprocess.run([cli, "c", src, dst], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CUDA device" in r.stderr and not os.path.exists(dst)
+        r = subprocess.run([cli, "d", src, dst], capture_output=True, text=True)
+        assert r.returncode != 0 and not os.path.exists(dst)
+
+
+def tmp_file(name, content):
+    import tempfile
+    path = os.path.join(tempfile.mkdtemp(prefix="lzs_b200_"), name)
+    if content is not None:
+        with open(path, "wb") as f:
+            f.write(content)
+    return path
 
 
 def test_product_never_links_the_oracle(B):
@@ -76,7 +93,7 @@ def test_product_never_links_the_oracle(B):
     assert "oracle" not in out and "lzs_ref" not in out
     srcs = []
     for root, _, files in os.walk(os.path.join(helpers.ROOT, "lzs-compression_b200")):
-        srcs += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".py"))]
+        srcs += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".py", ".cpp"))]
     for s in srcs:
         text = open(s).read()
         assert "oracle/" not in text and "liblzs_oracle" not in text and "liblzs_ref" not in text, s

@@ -59,3 +59,54 @@ def test_concatenated_chunk_streams_decode_with_reference_cli(tmp_path):
     d = tmp_path / "cat.out"
     subprocess.run([_bin("ref-lzs-decompress"), str(f), str(d)], check=True, timeout=600)
     assert d.read_bytes() == b"".join(chunks)
+
+
+# ---- the file CLI over the batch ABI (lzs-compression_b200/utils) ----
+
+def _cli():
+    path = os.path.join(helpers.ROOT, "lzs-compression_b200", "bin", "lzs-b200")
+    if not os.path.exists(path):
+        pytest.skip("lzs-b200 not built (make -C lzs-compression_b200)")
+    return path
+
+
+def _run(*args):
+    r = subprocess.run(list(args), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (args, r.stdout[-1000:], r.stderr[-1000:])
+
+
+def test_file_cli_chunked_output_is_decoded_by_the_reference_cli(tmp_path):
+    """`lzs-b200 c` writes back-to-back independent chunk streams: the reference's own
+    lzs-decompress restores the file, and so does `lzs-b200 d`, with the index (one batch) and
+    without it (one resumable stream, like the reference)."""
+    data = helpers.corpus(helpers.CORPUS_MIXED, 1, 300000, seed=0x5EED0000 + 8).tobytes() + b"odd tail"
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    comp, idx = tmp_path / "in.lzs", tmp_path / "in.lzsx"
+    _run(_cli(), "c", "-b", "16384", "-x", str(idx), str(src), str(comp))
+    # the file is exactly the concatenation of what lzs_compress gives for every chunk
+    o = helpers.oracle()
+    want = b"".join(o.compress(data[i:i + 16384]) for i in range(0, len(data), 16384))
+    assert comp.read_bytes() == want
+    for name, cmd in (("ref", [_bin("ref-lzs-decompress"), str(comp)]),
+                      ("b200_indexed", [_cli(), "d", "-x", str(idx), str(comp)]),
+                      ("b200_stream", [_cli(), "d", str(comp)])):
+        out = tmp_path / (name + ".out")
+        _run(*cmd, str(out))
+        assert out.read_bytes() == data, name
+
+
+def test_file_cli_single_chunk_equals_reference_compressor(tmp_path):
+    """With a chunk at least as large as the file, `lzs-b200 c` writes the very stream the
+    reference's lzs-compress writes; `lzs-b200 d` decodes the reference's file; empty file too."""
+    for tag, data in (("text", helpers.corpus(helpers.CORPUS_TEXT, 1, 50000, seed=0x5EED0000 + 9).tobytes()),
+                      ("empty", b"")):
+        src = tmp_path / (tag + ".bin")
+        src.write_bytes(data)
+        ours, theirs = tmp_path / (tag + ".b200.lzs"), tmp_path / (tag + ".ref.lzs")
+        _run(_cli(), "c", "-b", "1048576", str(src), str(ours))
+        _run(_bin("ref-lzs-compress"), str(src), str(theirs))
+        assert ours.read_bytes() == theirs.read_bytes(), tag
+        back = tmp_path / (tag + ".back")
+        _run(_cli(), "d", str(theirs), str(back))
+        assert back.read_bytes() == data, tag
