@@ -156,3 +156,90 @@ def test_gpu_incremental_batch_of_packets():
     # and the bulk path gives the same bytes (the fast way to do the same thing)
     assert B.compress_streams([pk[s * plen:(s + 1) * plen].tobytes() for s in range(8)]) == \
         [o.compress(pk[s * plen:(s + 1) * plen].tobytes()) for s in range(8)]
+
+
+@pytest.mark.gpu
+def test_gpu_flows_with_shared_history_across_packets():
+    """SURVEY.md section 8f-2 (RFC 1974 style): every flow compresses packet after packet through ONE
+    state block -- each packet runs to its END_MARKER, the history is kept (lzs-compression.c does
+    not reset it at the marker), so later packets refer back into earlier ones.  All flows advance
+    together through lzs_b200_compress_incremental_batch; every packet of every flow must equal
+    what the unmodified reference produces for the same call sequence, and the flow's packets,
+    fed one after the other to ONE decoder state, must give the plain bytes back."""
+    B = binding()
+    L = B.lib()
+    R = _ref()
+    ours, ref = D.StructCodec(L), D.StructCodec(R)
+    L.lzs_b200_compress_incremental_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+    n_flows, n_packets = 12, 5
+    rng = np.random.default_rng(5)
+    vocab = helpers.corpus(helpers.CORPUS_TEXT, 1, 4000, seed=0x5EED0000 + 12).tobytes()
+    flows = []
+    for f in range(n_flows):
+        pk = []
+        for k in range(n_packets):
+            a = int(rng.integers(0, 2500)); ln = int(rng.integers(40, 1400))
+            pk.append(vocab[a:a + ln] + bytes(rng.integers(0, 256, 8, dtype=np.uint8)))
+        flows.append(pk)
+
+    def fields(st):
+        return (ctypes.c_uint64 * 4).from_address(ctypes.addressof(st))
+
+    def status(st):
+        return ctypes.c_uint8.from_address(ctypes.addressof(st) + 32).value
+
+    cap = 2048
+    # reference: one flow at a time
+    want = []
+    for pk in flows:
+        st = ref.new(False)
+        outs = []
+        for p in pk:
+            src = np.frombuffer(p + b"\0" * 16, dtype=np.uint8).copy()
+            dst = np.zeros(cap, dtype=np.uint8)
+            f = fields(st)
+            f[0], f[1], f[2], f[3] = src.ctypes.data, dst.ctypes.data, len(p), cap
+            for _ in range(64):
+                R.lzs_compress_incremental(st, True)
+                if status(st) & D.END_MARKER:
+                    break
+            else:
+                raise AssertionError("reference never reached END_MARKER")
+            outs.append(dst[:cap - fields(st)[3]].tobytes())
+        want.append(outs)
+    assert sum(len(o) for o in want[0][1:]) < sum(len(helpers.oracle().compress(p)) for p in flows[0][1:]), \
+        "later packets should profit from the kept history"
+
+    # product: all flows together, packet by packet
+    states = [ours.new(False) for _ in flows]
+    got = [[] for _ in flows]
+    for k in range(n_packets):
+        srcs = [np.frombuffer(pk[k] + b"\0" * 16, dtype=np.uint8).copy() for pk in flows]
+        dsts = [np.zeros(cap, dtype=np.uint8) for _ in flows]
+        for st, s, d, pk in zip(states, srcs, dsts, flows):
+            f = fields(st)
+            f[0], f[1], f[2], f[3] = s.ctypes.data, d.ctypes.data, len(pk[k]), cap
+        todo = list(range(n_flows))
+        for _ in range(64):
+            arr = (ctypes.c_void_p * len(todo))(*[ctypes.addressof(states[i]) for i in todo])
+            B.check(L.lzs_b200_compress_incremental_batch(arr, len(todo), 1, None))
+            todo = [i for i in todo if not (status(states[i]) & D.END_MARKER)]
+            if not todo:
+                break
+        else:
+            raise AssertionError("flows never reached END_MARKER")
+        for i in range(n_flows):
+            got[i].append(dsts[i][:cap - fields(states[i])[3]].tobytes())
+    assert got == want
+
+    # decode: one decoder state per flow, packets fed one after the other (history kept across markers)
+    for pk, outs in zip(flows[:4], got[:4]):
+        st = ours.new(True)
+        back = b""
+        for p, c in zip(pk, outs):
+            src = np.frombuffer(c + b"\0" * 16, dtype=np.uint8).copy()
+            dst = np.zeros(len(p) + 64, dtype=np.uint8)
+            ret, stat, used = ours.call(True, st, src.ctypes.data, len(c), dst.ctypes.data, len(dst), False)
+            assert stat & D.END_MARKER and used == len(c)
+            back += dst[:ret].tobytes()
+        assert back == b"".join(pk)
