@@ -65,6 +65,18 @@ int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, 
                                      uint32_t *out_len, uint32_t n_streams, void *scratch,
                                      size_t scratch_bytes, void *stream);
 
+/* The same with one status byte per stream saying why its decoding stopped, in the values of
+ * LzsDecompressStatus_t (reference lzs.h:170-178; SURVEY.md section 8f-4, for untrusted packets):
+ *   LZS_D_STATUS_END_MARKER (0x04)             an end marker was reached (the normal case);
+ *   LZS_D_STATUS_NO_OUTPUT_BUFFER_SPACE (0x08) out_cap bytes were written and input was left;
+ *   LZS_D_STATUS_INPUT_STARVED (0x01)          the input ended first: nothing left, or the
+ *                                              remaining bits do not complete a token.
+ * The bytes and lengths are those of lzs_b200_decompress_batch_device; `status` may be NULL. */
+int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                            uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                            uint32_t *out_len, uint8_t *status, uint32_t n_streams,
+                                            void *scratch, size_t scratch_bytes, void *stream);
+
 /* Individual stages of the compressor, for tests and profiling:
  * K1 writes one record per input byte, (len << 11) | offset with len 0 or 2..12;
  * K2+K3 turn records + input into streams.  `counter` is device scratch of at least 16 bytes

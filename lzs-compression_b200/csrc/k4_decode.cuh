@@ -57,12 +57,16 @@ struct CarefulTag { static constexpr bool value = B; };
 template <int G>
 constexpr size_t k4_smem_bytes() { return static_cast<size_t>(kDecThreads / G) * kDecStreamSmem; }
 
+/* per-stream stop reasons, the values of LzsDecompressStatus_t (reference lzs.h:170-178) */
+constexpr uint32_t kDecStarved = 0x01u, kDecEndMarker = 0x04u, kDecNoSpace = 0x08u;
+
 template <int G>
 __global__ void __launch_bounds__(kDecThreads)
 k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
           const uint32_t *__restrict__ in_len, uint8_t *__restrict__ out,
           const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
-          uint32_t *__restrict__ out_len, uint32_t n_streams, uint32_t *__restrict__ next_stream)
+          uint32_t *__restrict__ out_len, uint32_t n_streams, uint32_t *__restrict__ next_stream,
+          uint8_t *__restrict__ status)
 {
     LZS_DYN_SMEM(uint8_t, smem);
     const uint32_t lane = lane_id();
@@ -265,7 +269,19 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
         }
         if (active && done) {
             for (uint32_t k = flushed + gl; k < pos; k += G) dst[k] = smem[ring0 + (k & (kDecRing - 1u))];
-            if (gl == 0) out_len[sid] = pos;
+            if (gl == 0) {
+                out_len[sid] = pos;
+                if (status != nullptr) {
+                    /* why the stream stopped, from where it stopped (a stop consumes nothing):
+                     * capacity reached with input left / nothing left / an end marker / a token
+                     * the remaining bits do not complete (include/lzs_b200.h) */
+                    const uint32_t left = end - cur;
+                    uint32_t       why = kDecStarved;
+                    if (left != 0u && pos >= cap) why = kDecNoSpace;
+                    else if (left >= 9u && !ext && (bits32(cur) >> 23) == 0x180u) why = kDecEndMarker;
+                    status[sid] = static_cast<uint8_t>(why);
+                }
+            }
             active = false;
         }
     }

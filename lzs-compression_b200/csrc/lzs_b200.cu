@@ -218,6 +218,15 @@ int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, 
                                      uint32_t *out_len, uint32_t n_streams, void *scratch,
                                      size_t scratch_bytes, void *stream)
 {
+    return lzs_b200_decompress_status_batch_device(in, in_off, in_len, out, out_off, out_cap, out_len, nullptr,
+                                                   n_streams, scratch, scratch_bytes, stream);
+}
+
+int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                            uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                            uint32_t *out_len, uint8_t *status, uint32_t n_streams,
+                                            void *scratch, size_t scratch_bytes, void *stream)
+{
     if (n_streams == 0) return LZS_B200_OK;
     if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len)
         return fail(LZS_B200_EINVAL, "null pointer");
@@ -237,19 +246,19 @@ int lzs_b200_decompress_batch_device(const uint8_t *in, const uint64_t *in_off, 
     switch (lanes) {
         case 4:
             lzs::k4_decode<4><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<4>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
             break;
         case 16:
             lzs::k4_decode<16><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<16>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
             break;
         case 32:
             lzs::k4_decode<32><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<32>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
             break;
         default:
             lzs::k4_decode<8><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<8>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
             break;
     }
     g_launches++;

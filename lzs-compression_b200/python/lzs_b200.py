@@ -76,6 +76,8 @@ def lib():
     host = [u8p, u64p, u32p, ctypes.c_uint64, u8p, u64p, u32p, u32p, ctypes.c_uint64, ctypes.c_uint32]
     L.lzs_b200_compress_batch_host.argtypes = host
     L.lzs_b200_decompress_batch_host.argtypes = host
+    L.lzs_b200_decompress_status_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp,
+                                                          ctypes.c_size_t, vp]
     L.lzs_b200_compress_packed_host.argtypes = [u8p, u64p, u32p, ctypes.c_uint64, u8p, ctypes.c_uint64, u64p, u32p,
                                                 ctypes.c_uint32, u64p]
     L.lzs_b200_corpus_fill_device.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
@@ -197,6 +199,36 @@ def decompress_streams(streams, caps):
     out_off, out_cap, out_span = layout(list(caps))
     dst, out_len = _host_batch(lib().lzs_b200_decompress_batch_host, src, in_off, in_len, out_off, out_cap, out_span)
     return [dst[int(o):int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+
+
+def decompress_streams_status(streams, caps, device="cuda:0"):
+    """Like decompress_streams, through the device entry point that also says why every stream
+    stopped (LzsDecompressStatus_t values).  Returns (list of bytes, list of status bytes)."""
+    import torch
+    L = lib()
+    streams = [bytes(s) for s in streams]
+    n = len(streams)
+    in_off, in_len, in_span = layout([len(s) for s in streams])
+    src = np.zeros(in_span + 64, dtype=np.uint8)
+    for o, s in zip(in_off, streams):
+        src[int(o):int(o) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    out_off, out_cap, out_span = layout(list(caps))
+    dev = torch.device(device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64 if a.dtype == np.uint64 else
+                                                               (np.int32 if a.dtype == np.uint32 else np.uint8))).to(dev)
+    d_src, d_inoff, d_inlen, d_outoff, d_outcap = t(src), t(in_off), t(in_len), t(out_off), t(out_cap)
+    d_dst = torch.zeros(out_span + 64, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    d_status = torch.full((max(n, 1),), 0xEE, dtype=torch.uint8, device=dev)
+    scratch = torch.empty(L.lzs_b200_decompress_scratch_bytes(), dtype=torch.uint8, device=dev)
+    check(L.lzs_b200_decompress_status_batch_device(
+        d_src.data_ptr(), d_inoff.data_ptr(), d_inlen.data_ptr(), d_dst.data_ptr(), d_outoff.data_ptr(),
+        d_outcap.data_ptr(), d_len.data_ptr(), d_status.data_ptr(), n, scratch.data_ptr(), scratch.numel(),
+        torch.cuda.current_stream(dev).cuda_stream))
+    torch.cuda.synchronize(dev)
+    dst, out_len, status = d_dst.cpu().numpy(), d_len.cpu().numpy(), d_status.cpu().numpy()
+    return ([dst[int(o):int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len[:n])],
+            [int(x) for x in status[:n]])
 
 
 # ---------------------------------------------------------------------- device batches

@@ -227,7 +227,12 @@ static uint32_t src_peek(const bitsrc_t *b, unsigned nbits)
 
 static size_t src_left(const bitsrc_t *b) { return b->nbits - b->pos; }
 
-size_t lzs_oracle_decompress(uint8_t *out, size_t out_cap, const uint8_t *in, size_t in_len)
+/* The same loop also reports which of its exits was taken, in the values of
+ * LzsDecompressStatus_t (lzs.h:170-178): 0x04 end marker (:255-261), 0x08 output full with input
+ * left (:200-203, :361-364), 0x01 input ended first (every "goto finish" on missing bits, and
+ * :189-192).  When the output fills up exactly as the input ends, the input check comes first,
+ * as at the top of the reference's loop. */
+size_t lzs_oracle_decompress_status(uint8_t *out, size_t out_cap, const uint8_t *in, size_t in_len, int *why)
 {
     bitsrc_t b;
     size_t   n = 0;
@@ -241,8 +246,9 @@ size_t lzs_oracle_decompress(uint8_t *out, size_t out_cap, const uint8_t *in, si
     for (;;) {
         unsigned length, k;
 
+        *why = 0x01;                            /* unless said otherwise below */
         if (src_left(&b) == 0) break;           /* :189-192                   */
-        if (n >= out_cap) break;                /* :200-203                   */
+        if (n >= out_cap) { *why = 0x08; break; }   /* :200-203               */
 
         if (!extended) {
             unsigned type = src_peek(&b, 1);
@@ -260,7 +266,7 @@ size_t lzs_oracle_decompress(uint8_t *out, size_t out_cap, const uint8_t *in, si
                 if (src_left(&b) < 7u) break;
                 offset = src_peek(&b, 7);
                 b.pos += 7;
-                if (offset == 0) break;         /* end marker, :255-261       */
+                if (offset == 0) { *why = 0x04; break; }   /* end marker, :255-261 */
             } else {                            /* long offset, :269-279      */
                 if (src_left(&b) < 11u) break;
                 offset = src_peek(&b, 11);
@@ -287,10 +293,19 @@ size_t lzs_oracle_decompress(uint8_t *out, size_t out_cap, const uint8_t *in, si
         for (k = 0; k < length; k++) {
             out[n] = (n >= offset) ? out[n - offset] : 0;
             n++;
-            if (n >= out_cap) return n;         /* :361-364                   */
+            if (n >= out_cap) {                 /* :361-364                   */
+                *why = src_left(&b) == 0 ? 0x01 : 0x08;
+                return n;
+            }
         }
     }
     return n;
+}
+
+size_t lzs_oracle_decompress(uint8_t *out, size_t out_cap, const uint8_t *in, size_t in_len)
+{
+    int why;
+    return lzs_oracle_decompress_status(out, out_cap, in, in_len, &why);
 }
 
 /* Upper bound used by callers for the output buffer; lzs.h:77. */

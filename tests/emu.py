@@ -33,7 +33,7 @@ def lib():
                            check=True)
         _lib = ctypes.CDLL(EMU_SO)
         _lib.emu_decode.argtypes = [c_u8p, c_u64p, c_u32p, c_u8p, c_u64p, c_u32p, c_u32p, ctypes.c_uint32,
-                                    ctypes.c_int, ctypes.c_uint]
+                                    ctypes.c_int, ctypes.c_uint, c_u8p]
         _lib.emu_match.argtypes = [c_u8p, c_u64p, c_u32p, c_u16p, ctypes.c_uint32, ctypes.c_uint]
         _lib.emu_parse_pack.argtypes = [c_u8p, c_u64p, c_u32p, c_u16p, c_u8p, c_u64p, c_u32p, c_u32p,
                                         ctypes.c_uint32]
@@ -78,14 +78,17 @@ def _collect(dst, out_off, caps, out_len, what):
     return res
 
 
-def decode(streams, caps, lanes=8, grid=2, align=16, lead=0, out_lead=0):
+def decode(streams, caps, lanes=8, grid=2, align=16, lead=0, out_lead=0, with_status=False):
     src, in_off, in_len = pack_streams(streams, align, lead)
     dst, out_off, out_cap = _out_layout(caps, out_lead)
     out_len = np.zeros(len(streams), dtype=np.uint32)
+    status = np.full(max(len(streams), 1), 0xEE, dtype=np.uint8)
     rc = lib().emu_decode(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(dst), _ptr(out_off, c_u64p),
-                          _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams), lanes, grid)
+                          _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams), lanes, grid,
+                          _ptr(status) if with_status else None)
     assert rc == 0
-    return _collect(dst, out_off, caps, out_len, "decoder")
+    got = _collect(dst, out_off, caps, out_len, "decoder")
+    return (got, [int(x) for x in status[:len(streams)]]) if with_status else got
 
 
 last_match_disorder = 0   # what the fast K1 launch recorded in the last match() (1: the safe launch ran)

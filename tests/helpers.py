@@ -74,6 +74,19 @@ class _Codec:
         r = self._d(_ptr(dst), cap, _ptr(src), len(data))
         return dst[:r].tobytes()
 
+    def decompress_status(self, data, cap):
+        """(bytes, why) -- oracle only: which exit of the decoder's loop was taken, as a
+        LzsDecompressStatus_t value (oracle/lzs_oracle.c:lzs_oracle_decompress_status)."""
+        f = self.lib.lzs_oracle_decompress_status
+        f.restype = ctypes.c_size_t
+        f.argtypes = [c_u8p, ctypes.c_size_t, c_u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]
+        data = bytes(data)
+        src = np.frombuffer(data + b"\0", dtype=np.uint8).copy()
+        dst = np.zeros(max(cap, 1), dtype=np.uint8)
+        why = ctypes.c_int(0)
+        r = f(_ptr(dst), cap, _ptr(src), len(data), ctypes.byref(why))
+        return dst[:r].tobytes(), why.value
+
     def run_streams(self, decompress, src, in_off, in_len, dst, out_off, out_cap, threads=1):
         """Batch driver (oracle/chunk_driver.c). Returns (out_len, seconds)."""
         n = len(in_len)

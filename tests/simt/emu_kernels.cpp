@@ -12,23 +12,23 @@
 template <int G>
 static void run_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                        const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
-                       unsigned grid)
+                       unsigned grid, uint8_t *status)
 {
     uint32_t counter = 0;
     simt::launch(dim3(grid), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<G>(), [&] {
-        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter);
+        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter, status);
     });
 }
 
 extern "C" int emu_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                           const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
-                          int lanes_per_stream, unsigned grid)
+                          int lanes_per_stream, unsigned grid, uint8_t *status)
 {
     switch (lanes_per_stream) {
-        case 4:  run_decode<4>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
-        case 8:  run_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
-        case 16: run_decode<16>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
-        case 32: run_decode<32>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid); break;
+        case 4:  run_decode<4>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid, status); break;
+        case 8:  run_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid, status); break;
+        case 16: run_decode<16>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid, status); break;
+        case 32: run_decode<32>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid, status); break;
         default: return -1;
     }
     return 0;

@@ -257,3 +257,35 @@ def test_structured_fuzz_against_cpu_codec(B):
     got = B.decompress_streams(damaged, caps)
     for s, c, g in zip(damaged, caps, got):
         assert g == cpu.decompress(s, c)
+
+
+def test_decode_status_words_against_oracle():
+    """per-stream stop reasons of the batch decoder on valid, truncated,
+    capacity-limited and random streams, against the oracle's statement of the reference loop."""
+    B = binding()
+    o = helpers.oracle()
+    rng = np.random.default_rng(23)
+    streams, caps = [], []
+    for i in range(300):
+        kind = [helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_PACKET, helpers.CORPUS_RANDOM][i % 4]
+        d = helpers.corpus(kind, 1, int(rng.integers(0, 3000)), first_index=i).tobytes()
+        c = o.compress(d)
+        mode = i % 5
+        if mode == 0:
+            streams.append(c); caps.append(len(d) + int(rng.integers(0, 40)))
+        elif mode == 1:
+            streams.append(c); caps.append(int(rng.integers(0, len(d) + 1)))
+        elif mode == 2:
+            streams.append(c[:int(rng.integers(0, len(c) + 1))]); caps.append(len(d) + 16)
+        elif mode == 3:
+            streams.append(c + bytes(rng.integers(0, 256, 5, dtype=np.uint8))); caps.append(len(d))
+        else:
+            streams.append(bytes(rng.integers(0, 256, int(rng.integers(0, 500)), dtype=np.uint8)))
+            caps.append(int(rng.integers(0, 4000)))
+    got, status = B.decompress_streams_status(streams, caps)
+    seen = set()
+    for s, c, g, st in zip(streams, caps, got, status):
+        want, why = o.decompress_status(s, c)
+        assert g == want and st == why, (len(s), c, st, why)
+        seen.add(why)
+    assert seen == {0x01, 0x04, 0x08}

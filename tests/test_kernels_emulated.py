@@ -61,6 +61,29 @@ def test_decode_random_bitstrings_match_oracle():
         assert g == o.decompress(s, c)
 
 
+@pytest.mark.parametrize("lanes", [4, 8, 32])
+def test_decode_status_words(cases, lanes):
+    """one status byte per stream saying why decoding stopped (end marker /
+    output full with input left / input ended first), against the oracle's statement of the
+    reference loop's exits -- on valid streams, capacity limits, truncations and random bits."""
+    o = helpers.oracle()
+    rng = np.random.default_rng(17)
+    streams, caps = [], []
+    for name, d in cases.items():
+        c = o.compress(d)
+        streams += [c, c, c[:len(c) // 2], c[:max(0, len(c) - 1)], c + b"\x55\xAA"]
+        caps += [len(d) + 8, max(0, len(d) - 3), len(d) + 8, len(d), len(d)]
+    streams += [rng.integers(0, 256, int(rng.integers(0, 300)), dtype=np.uint8).tobytes() for _ in range(40)]
+    caps += [int(rng.integers(0, 2000)) for _ in range(40)]
+    got, status = emu.decode(streams, caps, lanes=lanes, grid=3, with_status=True)
+    seen = set()
+    for s, c, g, st in zip(streams, caps, got, status):
+        want, why = o.decompress_status(s, c)
+        assert g == want and st == why, (len(s), c, st, why)
+        seen.add(why)
+    assert seen == {0x01, 0x04, 0x08}
+
+
 def test_match_finder_edge_cases(cases):
     names = list(cases)
     got, _ = emu.match([cases[k] for k in names])
