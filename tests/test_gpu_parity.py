@@ -289,3 +289,40 @@ def test_decode_status_words_against_oracle():
         assert g == want and st == why, (len(s), c, st, why)
         seen.add(why)
     assert seen == {0x01, 0x04, 0x08}
+
+
+def test_torch_front_end_ragged_tensors():
+    """ragged batches in torch.uint8 device tensors through lzs_torch
+    (current stream, no host round trip) give the oracle's bytes and decode back."""
+    import torch
+    from gpu_common import torch_front_end
+    lzs_torch = torch_front_end()
+    o = helpers.oracle()
+    rng = np.random.default_rng(31)
+    data = [helpers.corpus([helpers.CORPUS_TEXT, helpers.CORPUS_PACKET, helpers.CORPUS_BINARY][i % 3], 1,
+                           int(rng.integers(0, 5000)), first_index=i).tobytes() for i in range(64)]
+    off, pos = [], 0
+    for d in data:
+        off.append(pos)
+        pos += (len(d) + 15) // 16 * 16
+    buf = np.zeros(pos + 64, dtype=np.uint8)
+    for a, d in zip(off, data):
+        buf[a:a + len(d)] = np.frombuffer(d, dtype=np.uint8)
+    dev = torch.device("cuda:0")
+    t_buf = torch.from_numpy(buf).to(dev)
+    t_off = torch.tensor(off, dtype=torch.int64, device=dev)
+    t_len = torch.tensor([len(d) for d in data], dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):                       # any stream: the ops follow torch's current one
+        comp, comp_off, comp_len = lzs_torch.compress(t_buf, t_off, t_len)
+        plain, plain_len, status = lzs_torch.decompress(comp, comp_off, comp_len, t_off, t_len, with_status=True)
+    side.synchronize()
+    c, co, cl = comp.cpu().numpy(), comp_off.cpu().numpy(), comp_len.cpu().numpy()
+    for d, a, l in zip(data, co, cl):
+        assert c[int(a):int(a) + int(l)].tobytes() == o.compress(d)
+    p, pl = plain.cpu().numpy(), plain_len.cpu().numpy()
+    for d, a, l in zip(data, off, pl):
+        assert p[a:a + int(l)].tobytes() == d
+    # a stream decoded into exactly its size stops at "output full" unless it is empty (marker seen first)
+    assert all(int(s) in (0x04, 0x08) for s in status.cpu().numpy())
