@@ -261,9 +261,12 @@ __device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W,
  * it belongs to, so a foreign entry costs one shared-memory load. */
 #if defined(LZS_SIMT_EMU) && defined(LZS_K1_STATS)
 extern "C" unsigned long long g_k1_stats[8];   /* queries, steps, foreign, verified-fail, levels, run skips, max steps */
+extern "C" unsigned char g_k1_walk[1 << 22];    /* chain steps of the query at virtual position v (mod 4 Mi) */
 #define LZS_STAT(i, v) (g_k1_stats[i] += (v))
+#define LZS_STAT_WALK(v, steps) (g_k1_walk[(v) & ((1u << 22) - 1u)] = static_cast<unsigned char>((steps) > 255u ? 255u : (steps)))
 #else
 #define LZS_STAT(i, v) ((void)0)
+#define LZS_STAT_WALK(v, steps) ((void)0)
 #endif
 
 __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16_t *runs, const uint32_t *W,
@@ -282,11 +285,13 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
     uint32_t tag = e >> 11;
     uint32_t d = e & kLinkDistMask;
     uint32_t tot = 0;
+    uint32_t walked = 0;                                     /* statistics builds only */
     LZS_STAT(0, 1); LZS_STAT(4, 1);
     for (;;) {
         tot += d;
         if (d == 0 || tot > maxd) break;                     /* level k has no candidate: done */
         LZS_STAT(1, 1);
+        walked++;
         const uint32_t j = v - tot;
         e = lk[j & (kK1LinkRing - 1)];
         d = e & kLinkDistMask;
@@ -320,6 +325,8 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
         d = e & kLinkDistMask;
         tot = 0;
     }
+    LZS_STAT_WALK(v, walked);
+    (void)walked;
     return (best << kMatchOffBits) | bd;
 }
 
