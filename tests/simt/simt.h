@@ -338,6 +338,7 @@ static inline unsigned long long min(unsigned long long a, unsigned long long b)
 
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> static inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
 template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 
