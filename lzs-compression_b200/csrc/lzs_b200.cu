@@ -307,14 +307,27 @@ void lzs_b200_chunk_layout(uint64_t total, uint32_t chunk, uint64_t out_stride, 
 namespace {
 
 /* Grow-only device arena for the host-pointer entry points (one per device). */
+/* Result lengths of a slice go to the host by plain stores into mapped pinned memory.  A
+ * cudaMemcpyAsync for them would sit in the download engine's queue in ISSUE order, ahead of the
+ * bulk downloads of earlier slices that the host only issues once it has seen their lengths, and
+ * hold those back until the later slice's kernels are done (measured on B200, 1 GiB: first
+ * download finished at 51 ms instead of 8 ms). */
+__global__ void publish_lengths_kernel(uint32_t *__restrict__ host_mapped, const uint32_t *__restrict__ dev, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) host_mapped[i] = dev[i];
+}
+
 struct HostPath {
     std::mutex   mu;
     cudaStream_t stream = nullptr;          /* copies of small arrays, simple path        */
     cudaStream_t work[8] = {};              /* slice k: upload + kernels on work[k % 8]   */
     cudaStream_t down = nullptr;            /* downloads of finished slices               */
+    cudaStream_t up = nullptr;              /* uploads, in slice order, ahead of the kernels */
     void        *buf[11] = {};
     size_t       cap[11] = {};
-    uint32_t    *pinned_len = nullptr;      /* pinned staging for per-stream result lengths */
+    uint32_t    *pinned_len = nullptr;      /* pinned, device-mapped: per-stream result lengths */
+    uint32_t    *pinned_len_dev = nullptr;  /* the same memory as the device addresses it       */
     size_t       pinned_cap = 0;
 
     int reserve_pinned(size_t count)
@@ -322,10 +335,13 @@ struct HostPath {
         if (pinned_cap >= count) return LZS_B200_OK;
         if (pinned_len) cudaFreeHost(pinned_len);
         pinned_len = nullptr;
+        pinned_len_dev = nullptr;
         pinned_cap = 0;
-        if (cudaMallocHost(reinterpret_cast<void **>(&pinned_len), count * sizeof(uint32_t)) != cudaSuccess) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&pinned_len), count * sizeof(uint32_t), cudaHostAllocMapped) !=
+                cudaSuccess ||
+            cudaHostGetDevicePointer(reinterpret_cast<void **>(&pinned_len_dev), pinned_len, 0) != cudaSuccess) {
             cudaGetLastError();
-            return fail(LZS_B200_ENOMEM, "cudaMallocHost(%zu) failed", count * sizeof(uint32_t));
+            return fail(LZS_B200_ENOMEM, "cudaHostAlloc(%zu, mapped) failed", count * sizeof(uint32_t));
         }
         pinned_cap = count;
         return LZS_B200_OK;
@@ -357,8 +373,18 @@ int host_path(HostPath **out)
     if (!p.stream) {
         std::lock_guard<std::mutex> lock(p.mu);
         if (!p.stream) {
-            for (auto &w : p.work) CUDA_TRY(cudaStreamCreateWithFlags(&w, cudaStreamNonBlocking));
-            CUDA_TRY(cudaStreamCreateWithFlags(&p.down, cudaStreamNonBlocking));
+            /* Priorities fall from work[0] to work[7]: the decoder's slices run concurrently (it
+             * takes several to fill the GPU), and the earlier slice should win the SMs so that its
+             * download can start while the later ones are still being decoded.  `down` also runs
+             * the small gather kernel of the packed compressor: highest priority as well. */
+            int prio_lo = 0, prio_hi = 0;           /* numerically lower = more urgent */
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            for (int i = 0; i < 8; i++) {
+                const int pr = prio_hi + i < prio_lo ? prio_hi + i : prio_lo;
+                CUDA_TRY(cudaStreamCreateWithPriority(&p.work[i], cudaStreamNonBlocking, pr));
+            }
+            CUDA_TRY(cudaStreamCreateWithPriority(&p.down, cudaStreamNonBlocking, prio_hi));
+            CUDA_TRY(cudaStreamCreateWithFlags(&p.up, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
         }
     }
@@ -389,7 +415,7 @@ uint64_t slice_bytes(uint64_t total)
 /* First stream of every pipeline slice (slices are sized by UNcompressed bytes, `weight[s]`).
  * With `short_ends` (the compressor, which is kernel bound) the first and the last slice are a
  * quarter of the others: the first kernel starts after a short upload and the last download,
- * which has to wait for the last kernel, is short (measured on B200, 1 GiB: 67.2 -> 64.3 ms).
+ * which has to wait for the last kernel, is short (measured on B200, 1 GiB: 67 -> 64.5 ms).
  * The decompressor is bound by the download and measured slower that way (31.8 -> 35.7 ms), so it
  * keeps equal slices.  LZS_B200_SLICE_RAMP=0 turns the short ends off. */
 std::vector<uint32_t> plan_slices(const uint32_t *weight, uint32_t n, uint64_t total, bool short_ends)
@@ -477,16 +503,33 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
         CUDA_TRY(cudaMemcpyAsync(d_inlen, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_outoff, out_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_outcap, out_cap, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        std::vector<cudaEvent_t> ev(nslice + 1);
+        std::vector<cudaEvent_t> ev(nslice + 1), up_ev(nslice);
         for (auto &e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : up_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(ev[nslice], st));
         for (auto &w : p.work) CUDA_TRY(cudaStreamWaitEvent(w, ev[nslice], 0));
+        CUDA_TRY(cudaStreamWaitEvent(p.up, ev[nslice], 0));
         uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(p.buf[S_SCRATCH]) + kCounterBytes);
+        /* LZS_B200_TRACE=1 prints when every stage of every slice finished (ms from the start) */
+        const bool               trace = getenv("LZS_B200_TRACE") != nullptr;
+        std::vector<cudaEvent_t> tr(trace ? nslice * 4 + 1 : 0);
+        for (auto &e : tr) CUDA_TRY(cudaEventCreate(&e));
+        if (trace) cudaEventRecord(tr[nslice * 4], st);
         for (uint32_t k = 0; k < nslice && !rc; k++) {
             const uint32_t a = first[k], b = first[k + 1], cnt = b - a;
-            cudaStream_t   ws = p.work[k % 8u];
+            /* The decoder runs slice k on work[k % 8]: it needs several slices resident at once to
+             * fill the GPU.  The compressor's match finder fills the GPU with any slice, so its
+             * kernels run in slice order on ONE stream (uploads ahead of them on `up`): slices
+             * then finish one after the other and their downloads overlap the later slices'
+             * kernels, instead of all slices finishing together at the end. */
+            cudaStream_t   ws = decompress ? p.work[k % 8u] : p.work[0];
             const uint64_t lo = in_off[a], hi = in_off[b - 1] + in_len[b - 1];
-            if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, ws));
+            /* uploads in slice order on their own stream (issued on the work streams, the copy
+             * engine takes them in any order and an early slice can arrive after a later one) */
+            if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, p.up));
+            if (trace) cudaEventRecord(tr[k * 4 + 0], p.up);
+            CUDA_TRY(cudaEventRecord(up_ev[k], p.up));
+            CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
             if (decompress) {
                 rc = lzs_b200_decompress_batch_device(d_in, d_inoff + a, d_inlen + a, d_out, d_outoff + a, d_outcap + a,
                                                       d_outlen + a, cnt, d_cnt + k * 512, 256, ws);
@@ -498,7 +541,9 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
                                                           d_outcap + a, d_outlen + a, cnt, ws);
             }
             if (rc) break;
-            CUDA_TRY(cudaMemcpyAsync(p.pinned_len + a, d_outlen + a, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws));
+            if (trace) cudaEventRecord(tr[k * 4 + 1], ws);
+            publish_lengths_kernel<<<(cnt + 255u) / 256u, 256, 0, ws>>>(p.pinned_len_dev + a, d_outlen + a, cnt);
+            CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(ev[k], ws));
         }
         for (uint32_t k = 0; k < nslice && !rc; k++) {
@@ -508,17 +553,31 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
             uint64_t top = 0;
             for (uint32_t s2 = a; s2 < b; s2++)
                 if (out_len[s2] && out_off[s2] + out_len[s2] > top) top = out_off[s2] + out_len[s2];
+            if (trace) cudaEventRecord(tr[k * 4 + 2], p.down);
             if (top > out_off[a])
                 CUDA_TRY(cudaMemcpyAsync(out + out_off[a], d_out + out_off[a], top - out_off[a], cudaMemcpyDeviceToHost,
                                          p.down));
+            if (trace) cudaEventRecord(tr[k * 4 + 3], p.down);
         }
+        if (trace && !rc) {
+            cudaDeviceSynchronize();
+            for (uint32_t k = 0; k < nslice; k++) {
+                float t[4] = {0, 0, 0, 0};
+                for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tr[nslice * 4], tr[k * 4 + j]);
+                fprintf(stderr, "lzs (b200) trace: %s slice %u, %u streams: upload done %.2f  kernels done %.2f | download %.2f-%.2f\n",
+                        decompress ? "decompress" : "compress", k, first[k + 1] - first[k], t[0], t[1], t[2], t[3]);
+            }
+        }
+        for (auto &e : tr) cudaEventDestroy(e);
         cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
         for (auto &w : p.work) {
             cudaError_t e = cudaStreamSynchronize(w);
             if (e != cudaSuccess) e1 = e;
         }
         cudaError_t e3 = cudaStreamSynchronize(p.down);
+        cudaStreamSynchronize(p.up);                        /* nothing may still read the caller's buffer */
         for (auto &e : ev) cudaEventDestroy(e);
+        for (auto &e : up_ev) cudaEventDestroy(e);
         if (rc) return rc;
         CUDA_TRY(e1);
         CUDA_TRY(e2);
@@ -628,22 +687,37 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
     CUDA_TRY(cudaMemcpyAsync(d_inlen, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_slotoff, slot_off.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_slotcap, slot_cap.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    std::vector<cudaEvent_t> ev(nslice + 1);
+    std::vector<cudaEvent_t> ev(nslice + 1), up_ev(nslice);
     for (auto &e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : up_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(ev[nslice], st));
     for (auto &w : p.work) CUDA_TRY(cudaStreamWaitEvent(w, ev[nslice], 0));
+    CUDA_TRY(cudaStreamWaitEvent(p.up, ev[nslice], 0));
+    /* LZS_B200_TRACE=1 prints when every stage of every slice finished (ms from the start) */
+    const bool               trace = getenv("LZS_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tr(trace ? nslice * 6 + 1 : 0);
+    for (auto &e : tr) CUDA_TRY(cudaEventCreate(&e));
+    auto mark = [&](uint32_t k, int j, cudaStream_t s2) { if (trace) cudaEventRecord(tr[k * 6 + j], s2); };
+    if (trace) cudaEventRecord(tr[nslice * 6], st);
     for (uint32_t k = 0; k < nslice && !rc; k++) {
         const uint32_t a = first[k], b = first[k + 1], cnt = b - a;
-        cudaStream_t   ws = p.work[k % 8u];
+        cudaStream_t   ws = p.work[0];             /* kernels in slice order on one stream: see run_host_batch */
         const uint64_t lo = in_off[a], hi = in_off[b - 1] + in_len[b - 1];
-        if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, ws));
+        mark(k, 0, p.up);
+        if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, p.up));
+        mark(k, 1, p.up);
+        CUDA_TRY(cudaEventRecord(up_ev[k], p.up));
+        CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
         rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
                                          reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
+        mark(k, 2, ws);
         if (!rc)
             rc = lzs_b200_parse_pack_batch_device(d_in, d_inoff + a, d_inlen + a, matches, d_slots, d_slotoff + a,
                                                   d_slotcap + a, d_outlen + a, cnt, ws);
         if (rc) break;
-        CUDA_TRY(cudaMemcpyAsync(p.pinned_len + a, d_outlen + a, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws));
+        mark(k, 3, ws);
+        publish_lengths_kernel<<<(cnt + 255u) / 256u, 256, 0, ws>>>(p.pinned_len_dev + a, d_outlen + a, cnt);
+        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ev[k], ws));
     }
     uint64_t cursor = 0;
@@ -662,19 +736,33 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
             break;
         }
         CUDA_TRY(cudaMemcpyAsync(d_packoff + a, out_off + a, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, p.down));
+        mark(k, 4, p.down);
         gather_streams_kernel<<<cnt, 128, 0, p.down>>>(d_slots, d_slotoff + a, d_outlen + a, d_packed, d_packoff + a, cnt);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         if (cursor > begin)
             CUDA_TRY(cudaMemcpyAsync(out + begin, d_packed + begin, cursor - begin, cudaMemcpyDeviceToHost, p.down));
+        mark(k, 5, p.down);
     }
+    if (trace && !rc) {
+        cudaDeviceSynchronize();
+        for (uint32_t k = 0; k < nslice; k++) {
+            float t[6];
+            for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], tr[nslice * 6], tr[k * 6 + j]);
+            fprintf(stderr, "lzs (b200) trace: slice %u, %u streams: upload %.2f-%.2f  K1 -%.2f  K2K3 -%.2f | offsets up + gather from %.2f, download done %.2f\n",
+                    k, first[k + 1] - first[k], t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+    }
+    for (auto &e : tr) cudaEventDestroy(e);
     cudaError_t e1 = cudaSuccess;
     for (auto &w : p.work) {
         cudaError_t e = cudaStreamSynchronize(w);
         if (e != cudaSuccess) e1 = e;
     }
     cudaError_t e3 = cudaStreamSynchronize(p.down);
+    cudaStreamSynchronize(p.up);                            /* nothing may still read the caller's buffer */
     for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e : up_ev) cudaEventDestroy(e);
     if (rc) return rc;
     CUDA_TRY(e1);
     CUDA_TRY(e3);
