@@ -262,9 +262,12 @@ __device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W,
 #if defined(LZS_SIMT_EMU) && defined(LZS_K1_STATS)
 extern "C" unsigned long long g_k1_stats[8];   /* queries, steps, foreign, verified-fail, levels, run skips, max steps */
 extern "C" unsigned char g_k1_walk[1 << 22];    /* chain steps of the query at virtual position v (mod 4 Mi) */
+extern "C" unsigned char g_k1_foreign[1 << 22]; /* ... of which landed on a foreign entry (tag mismatch)     */
 #define LZS_STAT(i, v) (g_k1_stats[i] += (v))
 #define LZS_STAT_WALK(v, steps) (g_k1_walk[(v) & ((1u << 22) - 1u)] = static_cast<unsigned char>((steps) > 255u ? 255u : (steps)))
+#define LZS_STAT_FOREIGN(v) (g_k1_foreign[(v) & ((1u << 22) - 1u)] += g_k1_foreign[(v) & ((1u << 22) - 1u)] < 255u ? 1u : 0u)
 #else
+#define LZS_STAT_FOREIGN(v) ((void)0)
 #define LZS_STAT(i, v) ((void)0)
 #define LZS_STAT_WALK(v, steps) ((void)0)
 #endif
@@ -297,6 +300,7 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
         d = e & kLinkDistMask;
         if ((e >> 11) != tag) {                              /* foreign entry of this slot  */
             LZS_STAT(2, 1);
+            LZS_STAT_FOREIGN(v);
             if (d == 1u) {
                 /* its predecessor is the adjacent position: if j sits inside a run of one
                  * byte value that covers k bytes from j, every run member before j has j's
