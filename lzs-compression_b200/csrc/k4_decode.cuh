@@ -15,7 +15,7 @@
  * copy.  All 32/G groups of a warp advance in lock step under warp-uniform control
  * flow; one step takes a run of up to 7 literals (lane g looks at the token that
  * would start 9*g bits after the cursor; a ballot gives the length of the run) and
- * then at most one match or continuation token, and a step repeats that three times
+ * then at most one match or continuation token, and a step does kDecRounds of those
  * before it pays the fixed costs (votes, refill and flush checks) again.  The
  * compressed stream is staged in shared memory (64 words per stream, refilled 32
  * words at a time well ahead of the cursor), so a bit field at any position is two
@@ -45,11 +45,29 @@ constexpr uint32_t kDecRing = 2048;                 /* history bytes per stream 
 constexpr uint32_t kDecInWords = 64;                /* staged input words per stream        */
 constexpr uint32_t kDecStreamSmem = kDecRing + 4 * kDecInWords;
 #ifndef LZS_K4_ROUNDS
-#define LZS_K4_ROUNDS 4
+#define LZS_K4_ROUNDS 8
 #endif
 constexpr int      kDecRounds = LZS_K4_ROUNDS;      /* (literal run + one token) per step   */
 constexpr uint32_t kDecAhead = 24;                  /* words kept staged ahead of the cursor */
 static_assert(kDecRounds * 80 + 64 <= 32 * static_cast<int>(kDecAhead), "a step may not outrun the staged input");
+
+/* k mod m for 0 <= k < 16 and 1 <= m <= k (a match token carries at most 15 bytes): the
+ * quotient is floor((k + 0.5) / m), at least 1/30 away from the next integer, so an
+ * approximate reciprocal is exact here -- four predicated instructions instead of the ~18
+ * and a branch of a general 32-bit remainder (LZS_K4_GENERIC_MOD restores the latter). */
+__device__ __forceinline__ uint32_t small_mod(uint32_t k, uint32_t m)
+{
+#if defined(LZS_K4_GENERIC_MOD)
+    return k % m;
+#elif defined(LZS_SIMT_EMU)
+    const float q = (static_cast<float>(k) + 0.5f) * (1.0f / static_cast<float>(m));
+    return k - static_cast<uint32_t>(q) * m;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(static_cast<float>(m)));   /* one MUFU.RCP, no range fix-up */
+    return k - __float2uint_rz((static_cast<float>(k) + 0.5f) * r) * m;
+#endif
+}
 
 template <bool B>
 struct CarefulTag { static constexpr bool value = B; };
@@ -234,7 +252,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 v[t] = 0;
                 if (k < L) {
                     uint32_t kk = k;
-                    if (kk >= off) kk %= off;           /* overlap: periodic extension */
+                    if (kk >= off) kk = small_mod(kk, off);   /* overlap: periodic extension */
                     const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
                     if (s >= 0) v[t] = smem[ring0 + (static_cast<uint32_t>(s) & (kDecRing - 1u))];
                 }
