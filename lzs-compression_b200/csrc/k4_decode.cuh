@@ -15,8 +15,8 @@
  * copy.  All 32/G groups of a warp advance in lock step under warp-uniform control
  * flow; one step takes a run of up to 7 literals (lane g looks at the token that
  * would start 9*g bits after the cursor; a ballot gives the length of the run) and
- * then at most one match or continuation token, and a step does kDecRounds of those
- * before it pays the fixed costs (votes, refill and flush checks) again.  The
+ * then at most one match or continuation token, and a step does kDecRounds of those (fewer
+ * near the end of a stream) before it pays the fixed costs (votes, refill and flush checks) again.  The
  * compressed stream is staged in shared memory (64 words per stream, refilled 32
  * words at a time well ahead of the cursor), so a bit field at any position is two
  * shared-memory loads and a funnel shift.  Every collective uses
@@ -180,8 +180,17 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          * within one step, so the bound checks of the reference's loop are only compiled
          * into the "careful" variant used for the last steps of a stream. */
         bool       done = false;
-        const bool near_end = active && (end - cur < 96u * static_cast<uint32_t>(kDecRounds) + 64u ||
-                                         cap - pos < 24u * static_cast<uint32_t>(kDecRounds) + 8u);
+        /* How many rounds can every stream of the warp run without any bound check?  A round
+         * takes at most 80 bits and looks 64 + 32 bits ahead, and writes at most 22 bytes; the
+         * limits below are a little wider. */
+        uint32_t safe = static_cast<uint32_t>(kDecRounds);
+        if (active) {
+            const uint32_t bits = end - cur, room = cap - pos;
+            const uint32_t by_in = bits >= 64u ? (bits - 64u) / 96u : 0u;
+            const uint32_t by_out = room >= 8u ? (room - 8u) / 24u : 0u;
+            safe = umin32(safe, umin32(by_in, by_out));
+        }
+        safe = __reduce_min_sync(LZS_FULL_MASK, safe);
         auto one_round = [&](auto careful_tag) {
             constexpr bool kCareful = decltype(careful_tag)::value;
             /* ---- a run of literals, one per lane (token gl starts 9*gl bits after the cursor) ---- */
@@ -266,12 +275,18 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             pos += L;
             __syncwarp();
         };
-        if (__any_sync(LZS_FULL_MASK, near_end)) {
-#pragma unroll
-            for (int round = 0; round < kDecRounds; round++) one_round(CarefulTag<true>{});
-        } else {
+        /* Full steps while every stream of the warp is far from its end; as many rounds as are
+         * still safe (one copy of the round in a loop) when one of them is closer -- with
+         * 1500-byte packets that is most of the time -- and the careful variant, one round per
+         * step, only for the last tokens of a stream. */
+        if (safe >= static_cast<uint32_t>(kDecRounds)) {
 #pragma unroll
             for (int round = 0; round < kDecRounds; round++) one_round(CarefulTag<false>{});
+        } else if (safe != 0u) {
+#pragma unroll 1
+            for (uint32_t round = 0; round < safe; round++) one_round(CarefulTag<false>{});
+        } else {
+            one_round(CarefulTag<true>{});
         }
 
         /* flush once per step (a step adds at most kDecRounds * 22 bytes, far less than the ring) */
