@@ -412,6 +412,20 @@ uint64_t slice_bytes(uint64_t total)
     return v;
 }
 
+/* The compressor's parse/pack kernel (one warp per stream: a slice of it lasts as long as its
+ * slowest stream, ~3 ms for 64 KiB streams, however few there are) runs on a second, less urgent
+ * stream behind the match finder's, so that it shares the SMs with the next slice's match finder
+ * instead of holding it up.  LZS_B200_K23_STREAM=0 puts both back on one stream. */
+bool parse_on_side_stream()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_K23_STREAM");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 /* First stream of every pipeline slice (slices are sized by UNcompressed bytes, `weight[s]`).
  * With `short_ends` (the compressor, which is kernel bound) the first and the last slice are a
  * quarter of the others: the first kernel starts after a short upload and the last download,
@@ -536,6 +550,11 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
             } else {
                 rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
                                                  reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
+                if (!rc && parse_on_side_stream()) {
+                    CUDA_TRY(cudaEventRecord(up_ev[k], ws));            /* reused: the upload has been waited for */
+                    ws = p.work[1];
+                    CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
+                }
                 if (!rc)
                     rc = lzs_b200_parse_pack_batch_device(d_in, d_inoff + a, d_inlen + a, matches, d_out, d_outoff + a,
                                                           d_outcap + a, d_outlen + a, cnt, ws);
@@ -711,6 +730,11 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
         rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
                                          reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
         mark(k, 2, ws);
+        if (!rc && parse_on_side_stream()) {
+            CUDA_TRY(cudaEventRecord(up_ev[k], ws));                    /* reused: the upload has been waited for */
+            ws = p.work[1];
+            CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
+        }
         if (!rc)
             rc = lzs_b200_parse_pack_batch_device(d_in, d_inoff + a, d_inlen + a, matches, d_slots, d_slotoff + a,
                                                   d_slotcap + a, d_outlen + a, cnt, ws);
