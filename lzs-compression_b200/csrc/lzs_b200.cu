@@ -394,11 +394,15 @@ int host_path(HostPath **out)
 
 enum { S_IN, S_OUT, S_INOFF, S_INLEN, S_OUTOFF, S_OUTCAP, S_OUTLEN, S_SCRATCH, S_COUNTERS, S_PACKED, S_PACKOFF };
 
-/* Uncompressed bytes per pipeline slice: a quarter of the batch, between 32 and 256 MiB
- * (measured on B200, 1 GiB batch: 256 MiB slices give 86 ms compress / 43 ms decompress
- * against 105 / 121 ms with 16 MiB slices -- the decoder needs thousands of streams per
- * launch).  LZS_B200_SLICE_MIB overrides, for tuning. */
-uint64_t slice_bytes(uint64_t total)
+/* Uncompressed bytes per pipeline slice.  Compressor: a quarter of the batch, between 32 and
+ * 256 MiB (its kernels run slice after slice, and every slice pays the tail of the match finder
+ * and the latency of the parse kernel's slowest stream; measured on B200, 1 GiB: 128 / 192 / 256 /
+ * 384 MiB slices -> 66.0 / 62.1 / 60.9 / 64.2 ms).  Decompressor: 64 MiB -- its slices run
+ * concurrently on eight streams, so small slices cost nothing on the GPU and let the first
+ * download start early (1 GiB: 16 / 32 / 48 / 64 / 96 / 128 / 256 MiB -> 59.5 / 35.5 / 29.2 / 28.8 /
+ * 29.4 / 30.5 / 32.0 ms; below 64 MiB slices start to queue behind each other on the eight
+ * streams).  LZS_B200_SLICE_MIB overrides both, for tuning. */
+uint64_t slice_bytes(uint64_t total, bool decompress)
 {
     static long env_mib = -1;
     if (env_mib < 0) {
@@ -406,6 +410,7 @@ uint64_t slice_bytes(uint64_t total)
         env_mib = e ? atol(e) : 0;
     }
     if (env_mib > 0) return static_cast<uint64_t>(env_mib) << 20;
+    if (decompress) return 64ull << 20;
     uint64_t v = total / 4;
     if (v < (32ull << 20)) v = 32ull << 20;
     if (v > (256ull << 20)) v = 256ull << 20;
@@ -416,14 +421,16 @@ uint64_t slice_bytes(uint64_t total)
  * slowest stream, ~3 ms for 64 KiB streams, however few there are) runs on a second, less urgent
  * stream behind the match finder's, so that it shares the SMs with the next slice's match finder
  * instead of holding it up.  LZS_B200_K23_STREAM=0 puts both back on one stream. */
-bool parse_on_side_stream()
+int parse_side_streams()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("LZS_B200_K23_STREAM");
         v = e ? atoi(e) : 1;
+        if (v < 0) v = 0;
+        if (v > 7) v = 7;
     }
-    return v != 0;
+    return v;
 }
 
 /* First stream of every pipeline slice (slices are sized by UNcompressed bytes, `weight[s]`).
@@ -439,7 +446,7 @@ std::vector<uint32_t> plan_slices(const uint32_t *weight, uint32_t n, uint64_t t
         const char *e = getenv("LZS_B200_SLICE_RAMP");
         ramp = e ? atoi(e) : 1;
     }
-    const uint64_t big = slice_bytes(total);
+    const uint64_t big = slice_bytes(total, !short_ends);   /* short ends: the compressor */
     const uint64_t small = big / 4;
     std::vector<uint64_t> plan;
     uint64_t              left = total;
@@ -550,9 +557,9 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
             } else {
                 rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
                                                  reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
-                if (!rc && parse_on_side_stream()) {
+                if (!rc && parse_side_streams() > 0) {
                     CUDA_TRY(cudaEventRecord(up_ev[k], ws));            /* reused: the upload has been waited for */
-                    ws = p.work[1];
+                    ws = p.work[1 + k % static_cast<uint32_t>(parse_side_streams())];
                     CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
                 }
                 if (!rc)
@@ -730,9 +737,9 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
         rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
                                          reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
         mark(k, 2, ws);
-        if (!rc && parse_on_side_stream()) {
+        if (!rc && parse_side_streams() > 0) {
             CUDA_TRY(cudaEventRecord(up_ev[k], ws));                    /* reused: the upload has been waited for */
-            ws = p.work[1];
+            ws = p.work[1 + k % static_cast<uint32_t>(parse_side_streams())];
             CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
         }
         if (!rc)
