@@ -8,8 +8,9 @@
  * It is never part of the product and proves nothing about performance or about
  * races between warps; the -m gpu tests run the real kernels on real hardware.
  *
- * Model: one thread block at a time; every CUDA thread is a fibre (ucontext) on
- * one OS thread; fibres switch only inside warp collectives, __syncthreads() and
+ * Model: one thread block at a time; every CUDA thread is a fibre (a private stack and a
+ * hand-written register switch on x86-64 -- swapcontext makes a system call per switch -- or
+ * ucontext elsewhere) on one OS thread; fibres switch only inside warp collectives, __syncthreads() and
  * simt_yield().  Collectives rendezvous per (warp, member mask), so sub-warp
  * groups that use their own masks work as on Volta+ independent scheduling.
  */
@@ -53,8 +54,17 @@ struct Rdv {                        /* one rendezvous per (warp, mask) */
     uint64_t vals[32], snap[32];
 };
 
+#if defined(__x86_64__)
+#define LZS_SIMT_FAST_SWITCH 1
+extern "C" void simt_switch(void **save_sp, void *load_sp);
+#endif
+
 struct Fiber {
+#ifdef LZS_SIMT_FAST_SWITCH
+    void      *sp = nullptr;
+#else
     ucontext_t ctx;
+#endif
     char      *stack = nullptr;
     bool       done = false;
     uint3      tid;
@@ -67,7 +77,11 @@ struct Block {
     unsigned  bar_arrived = 0;
     uint64_t  bar_round = 0;
     std::map<int, std::pair<unsigned, uint64_t>> named;   /* id -> (arrived, round) */
+#ifdef LZS_SIMT_FAST_SWITCH
+    void      *sched_sp = nullptr;
+#else
     ucontext_t sched;
+#endif
     int        current = -1;
     std::function<void()> body;
     std::vector<uint8_t> dyn_smem;
@@ -80,7 +94,11 @@ extern dim3   g_blockDim, g_gridDim;
 inline void yield()
 {
     Block *b = g_block;
+#ifdef LZS_SIMT_FAST_SWITCH
+    simt_switch(&b->fibers[b->current].sp, b->sched_sp);
+#else
     swapcontext(&b->fibers[b->current].ctx, &b->sched);
+#endif
 }
 
 inline unsigned lane_id() { return g_threadIdx.x & 31u; }
