@@ -59,6 +59,15 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t *p, const uint
     return __funnelshift_r(lo, hi, sh);
 }
 
+/* Orders this thread's earlier shared-memory accesses before its later ones as seen by the
+ * other threads of the block (release before publishing a counter, acquire after reading one). */
+__device__ __forceinline__ void cta_fence()
+{
+#ifndef LZS_SIMT_EMU
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+}
+
 /* Body of a spin-wait on a shared-memory flag. */
 __device__ __forceinline__ void spin_pause()
 {
@@ -66,6 +75,25 @@ __device__ __forceinline__ void spin_pause()
     simt_yield();
 #else
     __nanosleep(20);
+#endif
+}
+
+/* The same with a back-off: a warp that polls steals issue slots from the warps it is waiting
+ * for, so the pause doubles with every unsuccessful poll (`ns` is the caller's, reset per wait). */
+#ifndef LZS_SPIN_NS_MIN
+#define LZS_SPIN_NS_MIN 32
+#endif
+#ifndef LZS_SPIN_NS_MAX
+#define LZS_SPIN_NS_MAX 64
+#endif
+__device__ __forceinline__ void spin_backoff(uint32_t &ns)
+{
+#ifdef LZS_SIMT_EMU
+    (void)ns;
+    simt_yield();
+#else
+    __nanosleep(ns);
+    if (ns < LZS_SPIN_NS_MAX) ns *= 2u;
 #endif
 }
 

@@ -28,9 +28,7 @@ def lib():
     global _lib
     if _lib is None:
         if _needs_build():
-            # fewer query warps than the product launches (a parallelism knob, no logic depends on it):
-            # every fibre costs the emulator time
-            subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DLZS_K1_QW=6", "-I" + SIMT_DIR, "-o", EMU_SO,
+            subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I" + SIMT_DIR, "-o", EMU_SO,
                             os.path.join(SIMT_DIR, "emu_kernels.cpp"), os.path.join(SIMT_DIR, "simt.cpp")],
                            check=True)
         _lib = ctypes.CDLL(EMU_SO)

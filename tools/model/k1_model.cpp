@@ -13,6 +13,7 @@ static int SLOTS_LOG = 11;
 static int TAGBITS = 5;
 
 static int HASHMODE = 0;
+static int GALLOP = 2;
 static inline uint32_t rolling_hash(const uint8_t *p, int k)
 {
     // groups of levels as the build warps compute them: {2,3,4} {5,6,7} {8,9,10} {11,12}
@@ -73,9 +74,10 @@ int main(int argc, char **argv)
     SLOTS_LOG = argc > 3 ? atoi(argv[3]) : 11;
     TAGBITS = argc > 4 ? atoi(argv[4]) : 5;
     HASHMODE = argc > 5 ? atoi(argv[5]) : 0;
+    GALLOP = argc > 6 ? atoi(argv[6]) : 2;
     const int n = 65536;
     std::vector<uint8_t> buf(n + 64, 0);
-    Stats cur, v1, v2, v3;
+    Stats cur, v1, v2, v3, v4;
     double lenhist[13] = {0};
     for (int s = 0; s < nstreams; s++) {
         memset(buf.data(), 0, buf.size());
@@ -107,7 +109,7 @@ int main(int argc, char **argv)
                 }
             }
         // queries
-        std::vector<int> c0(n), c1(n), c2(n), c3(n), needB(n);
+        std::vector<int> c0(n), c1(n), c2(n), c3(n), c4(n), needB(n), lenbest(n);
         for (int i = 1; i + 12 <= n; i++) {
             const int M = 12, maxd = std::min(W, i);
             // ---- V0: current upward walk; steps = chain hops (LDS of entries)
@@ -131,7 +133,7 @@ int main(int argc, char **argv)
                     if (!found || best >= M) break;
                     k = best + 1;
                 }
-                c0[i] = steps;
+                c0[i] = steps; lenbest[i] = best;
                 lenhist[best]++;
             }
             // ---- V1: E-mask (pred tag known from head), start at top level with immediate tag hit
@@ -182,6 +184,31 @@ int main(int argc, char **argv)
                 if (variant == 1) { c1[i] = steps; if (resolved) v1.resolvedA++; }
                 else { c2[i] = steps; if (resolved) v2.resolvedA++; needB[i] = resolved ? 0 : (steps - (kE ? 3 : 1)); }
             }
+            // ---- V4: upward for the first GALLOP probes, then binary search over the remaining levels
+            {
+                int steps = 0, best = 0, probes = 0;
+                int lo = 2, hi = M;                 // levels still undecided: lo..hi (hi < lo: done)
+                while (lo <= hi && best < M) {
+                    int k = (probes < GALLOP) ? lo : (lo + hi + 1) / 2;
+                    probes++;
+                    int tot = 0, d = L[k].d1[i];
+                    bool found = false;
+                    steps++;
+                    while (d && tot + d <= maxd) {
+                        tot += d;
+                        int j = i - tot;
+                        steps++;
+                        d = L[k].d1[j];
+                        if (L[k].tag[j] != L[k].tag[i]) continue;
+                        int l = lcp(&buf[i], &buf[j], M);
+                        if (l < k) continue;
+                        best = l; found = true; break;
+                    }
+                    if (found) lo = best + 1; else hi = k - 1;
+                }
+                c4[i] = steps;
+                if (best != (int)lenbest[i]) { fprintf(stderr, "V4 mismatch at %d: %d vs %d\n", i, best, lenbest[i]); exit(1); }
+            }
             // ---- V3: plain upward walk (V0) but with collapse skip
             {
                 int k = 2, steps = 0, best = 0;
@@ -212,7 +239,7 @@ int main(int argc, char **argv)
                 st.maxsum += mx; st.passes++;
             }
         };
-        acc(cur, c0); acc(v1, c1); acc(v2, c2); acc(v3, c3);
+        acc(cur, c0); acc(v1, c1); acc(v2, c2); acc(v3, c3); acc(v4, c4);
         // phase B for V2: compact unresolved positions of a 448 tile into groups of 32
         for (int t = 32; t + 448 <= n - 12; t += 448) {
             std::vector<int> list;
@@ -233,6 +260,7 @@ int main(int argc, char **argv)
     };
     pr("V0 current upward", cur);
     pr("V3 upward+collapse", v3);
+    pr("V4 gallop+binary", v4);
     pr("V1 mask start", v1);
     pr("V2 mask start+collapse", v2);
     printf("  V2 two-phase: walkers %.1f%%  B steps/walker %.2f  B warp-max %.2f  B passes per 448-tile %.2f -> B max-steps per pos %.3f\n",

@@ -27,6 +27,12 @@ def main():
     if a.lanes:
         B.check(B.lib().lzs_b200_set_decode_lanes(a.lanes))
     db = B.DeviceBatch(total, a.chunk)
+    for kind in a.kind.split(","):
+        a.kind = kind
+        run(a, db, total)
+
+
+def run(a, db, total):
     db.fill(KINDS[a.kind], 0x5EED0002)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
