@@ -86,7 +86,16 @@ constexpr uint32_t kK1Depth = LZS_K1_DEPTH; /* tiles the build warps may be ahea
  * multiple of 32 (every stream starts on a batch boundary, so a batch never straddles a ring
  * wrap and the positions a last batch inserts past the end of its stream belong to no stream). */
 constexpr uint32_t kK1StreamGap = 16 + 31;
-constexpr int      kK1BuildWarps = kK1Levels + 1;   /* one warp per level + the run-table warp */
+#ifndef LZS_K1_LPW
+#define LZS_K1_LPW 1                        /* levels per build warp */
+#endif
+constexpr int      kK1Lpw = LZS_K1_LPW;
+#ifndef LZS_K1_GROUPED
+#define LZS_K1_GROUPED 1                    /* 1: the group code (compile-time levels, exchanges in flight while the next batch is hashed) also for one level per warp */
+#endif
+constexpr bool     kK1Grouped = LZS_K1_GROUPED != 0;
+/* one warp per level + the run-table warp, or a group of levels per warp (the last one also builds the run table) */
+constexpr int      kK1BuildWarps = kK1Lpw == 1 ? kK1Levels + 1 : (kK1Levels + kK1Lpw - 1) / kK1Lpw;
 #ifndef LZS_K1_QW
 #define LZS_K1_QW 16
 #endif
@@ -217,6 +226,101 @@ __device__ __forceinline__ uint32_t k1_build_level(uint32_t *hd, uint16_t *lk, c
     return disorder;
 }
 
+/* Hashes of the k-grams that start the 12 bytes (w0, w1, w2), k = 2..12.  Bits 31..21 are the
+ * table slot, bits 20..16 a 5-bit tag kept beside every chain link so that a query can reject
+ * most foreign entries of its slot without touching their bytes.  A build warp needs the hashes
+ * of a few consecutive levels of the same position: the first is made from the masked words, each
+ * further one by mixing one more byte into the previous (one LOP3, one IMAD).  Nobody else ever
+ * computes these hashes (a query compares the tags stored beside the links), so the levels need
+ * not agree on a formula. */
+constexpr uint32_t kHashC1 = 0x9E3779B1u, kHashC2 = 0x85EBCA77u;
+__device__ __forceinline__ uint32_t gram_mask(int bytes) { return bytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * bytes)) - 1u); }
+__device__ __forceinline__ uint32_t k1_hash_start(int k, uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    if (k <= 4) return (w0 & gram_mask(k)) * kHashC1;
+    if (k <= 8) return ((w0 * kHashC1) ^ (w1 & gram_mask(k - 4))) * kHashC2;
+    return ((((w0 * kHashC1) ^ w1) * kHashC2) ^ (w2 & gram_mask(k - 8))) * kHashC1;
+}
+/* hash of the k-gram from the hash of the (k-1)-gram: byte k-1 comes in where it sits in its word */
+__device__ __forceinline__ uint32_t k1_hash_roll(int k, uint32_t h, uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const int      b = k - 1;
+    const uint32_t w = b < 4 ? w0 : (b < 8 ? w1 : w2);
+    return (h ^ (w & (0xFFu << (8 * (b & 3))))) * kHashC1;
+}
+
+/* Insert the positions of one tile into the tables of levels K0 .. K0+NL-1, in order, and record
+ * for each position and level the distance to the previous position of the same slot (0 = none
+ * within 2047).  Executed by one whole warp; vt = virtual position of the tile start, a multiple
+ * of 32.  One atomic exchange per lane and level puts the position into the slot's head and
+ * returns its predecessor: lanes of one batch that share a slot are served in ascending lane
+ * (= position) order, so each receives the lane before it and the highest one stays in the head.
+ * That order is what sm_100a does (tools/micro/atoms_exch.cu), not something PTX promises, so the
+ * fast kernel only RECORDS whether a lane ever received a higher lane of its own batch (the
+ * returned flag; nothing in the loop waits for it) and the safe kernel (kSafe: every batch
+ * repaired with k1_relink, exact for any service order) re-does the whole batch of streams if that
+ * was ever seen.  The last batch of a stream runs all 32 lanes: the positions past the end sit in
+ * the gap before the next stream, where no query ever looks (a candidate is valid only up to the
+ * query's own position inside its stream).  The levels of a group are independent of each other,
+ * so their exchanges are in flight together. */
+template <int K0, int NL, bool kSafe>
+__device__ __forceinline__ uint32_t k1_build_group(uint32_t *heads, uint16_t *links, const uint32_t *W, uint32_t vt,
+                                                   uint32_t tile_n)
+{
+    const uint32_t  lane = lane_id();
+    const uint32_t *Wl = W + lane;
+    uint32_t       *hd = heads + (K0 - 2) * kK1Slots;
+    uint16_t       *lk0 = links + (K0 - 2) * kK1LinkRing + lane;
+    uint32_t        disorder = 0;
+    /* Software pipeline: the exchanges of a batch are issued, then the grams of the NEXT batch are
+     * loaded and hashed while the exchanges are under way, and only then are their results turned
+     * into links -- a warp with several levels is bound by what it issues, not by the round trip
+     * of an exchange (exchanges of one warp reach the table in program order). */
+    uint32_t h[NL];
+    {
+        const uint32_t x = vt & (kK1WRing - 1);
+        const uint32_t w0 = Wl[x], w1 = Wl[x + 4], w2 = Wl[x + 8];
+        h[0] = k1_hash_start(K0, w0, w1, w2);
+#pragma unroll
+        for (int l = 1; l < NL; l++) h[l] = k1_hash_roll(K0 + l, h[l - 1], w0, w1, w2);
+    }
+#pragma unroll 2
+    for (uint32_t b = 0; b < tile_n; b += 32) {
+        const uint32_t vb = vt + b;                       /* warp-uniform, a multiple of 32 */
+        const uint32_t pos = vb | lane;
+        uint16_t      *lk = lk0 + (vb & (kK1LinkRing - 1));
+        uint32_t       old[NL], tagbits[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            uint32_t *slot = hd + l * kK1Slots + (h[l] >> kSlotShift);
+            old[l] = smem_exch(slot, pos);
+            if (kSafe) {
+                __syncwarp();
+                old[l] = k1_relink(slot, h[l] >> kSlotShift, old[l], vb, pos);
+            }
+            tagbits[l] = (h[l] >> 5) & 0xF800u;           /* tag << 11 */
+        }
+        {
+            /* the batch after this one (past the tile's end: grams that are there anyway) */
+            const uint32_t x = (vb + 32u) & (kK1WRing - 1);
+            const uint32_t w0 = Wl[x], w1 = Wl[x + 4], w2 = Wl[x + 8];
+            h[0] = k1_hash_start(K0, w0, w1, w2);
+#pragma unroll
+            for (int l = 1; l < NL; l++) h[l] = k1_hash_roll(K0 + l, h[l - 1], w0, w1, w2);
+        }
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            const uint32_t dist = pos - old[l];
+            if (!kSafe) disorder |= dist;                 /* sign bit: received a LATER position, not the order assumed */
+            uint32_t e = tagbits[l];
+            if (dist <= kWindow) e |= dist;               /* further than the window: no link */
+            lk[l * kK1LinkRing] = static_cast<uint16_t>(e);
+        }
+        __syncwarp();                                     /* batch after batch, also formally */
+    }
+    return disorder >> 31;
+}
+
 /* Run table of one tile (one whole warp).  For every position p it records how far back
  * the run of identical bytes containing p starts (0 = p starts a run, capped at 4095)
  * and how many identical bytes follow from p (capped at 12).  Positions p-1 and p have the
@@ -252,6 +356,66 @@ __device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W,
         prev_byte = __shfl_sync(LZS_FULL_MASK, byte, 31);
     }
 }
+
+/* One build warp's share of a tile: its group of levels, and for the last group the run table. */
+template <bool kSafe>
+__device__ __forceinline__ uint32_t k1_build_tile(uint32_t warp, uint32_t *heads, uint16_t *links, uint16_t *runs,
+                                                  const uint32_t *W, const K1Tile &d)
+{
+    const uint32_t vt = d.v0 + d.t0;
+    uint32_t       dis = 0;
+#if LZS_K1_LPW == 3
+    switch (warp) {
+        case 0: dis = k1_build_group<2, 3, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 1: dis = k1_build_group<5, 3, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 2: dis = k1_build_group<8, 3, kSafe>(heads, links, W, vt, d.tile_n); break;
+        default:
+            dis = k1_build_group<11, 2, kSafe>(heads, links, W, vt, d.tile_n);
+            k1_build_runs(runs, W, d.v0, d.t0, d.tile_n);
+            break;
+    }
+#elif LZS_K1_LPW == 2
+    switch (warp) {
+        case 0: dis = k1_build_group<2, 2, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 1: dis = k1_build_group<4, 2, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 2: dis = k1_build_group<6, 2, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 3: dis = k1_build_group<8, 2, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 4: dis = k1_build_group<10, 2, kSafe>(heads, links, W, vt, d.tile_n); break;
+        default:
+            dis = k1_build_group<12, 1, kSafe>(heads, links, W, vt, d.tile_n);
+            k1_build_runs(runs, W, d.v0, d.t0, d.tile_n);
+            break;
+    }
+#elif LZS_K1_LPW == 1
+    switch (warp) {
+        case 0: dis = k1_build_group<2, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 1: dis = k1_build_group<3, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 2: dis = k1_build_group<4, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 3: dis = k1_build_group<5, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 4: dis = k1_build_group<6, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 5: dis = k1_build_group<7, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 6: dis = k1_build_group<8, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 7: dis = k1_build_group<9, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 8: dis = k1_build_group<10, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 9: dis = k1_build_group<11, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 10: dis = k1_build_group<12, 1, kSafe>(heads, links, W, vt, d.tile_n); break;
+        default: k1_build_runs(runs, W, d.v0, d.t0, d.tile_n); break;
+    }
+#elif LZS_K1_LPW == 4
+    switch (warp) {
+        case 0: dis = k1_build_group<2, 4, kSafe>(heads, links, W, vt, d.tile_n); break;
+        case 1: dis = k1_build_group<6, 4, kSafe>(heads, links, W, vt, d.tile_n); break;
+        default:
+            dis = k1_build_group<10, 3, kSafe>(heads, links, W, vt, d.tile_n);
+            k1_build_runs(runs, W, d.v0, d.t0, d.tile_n);
+            break;
+    }
+#else
+#error "LZS_K1_LPW must be 1, 2, 3 or 4"
+#endif
+    return dis;
+}
+
 
 /* One query = a single flat loop of chain steps (no nested loops, so lanes of a warp
  * stay together).  Levels are tried upwards: a verified candidate of length l at level
@@ -521,7 +685,9 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             if (g >= kK1Depth) mbar_wait(&s_empty[buf], (g / kK1Depth - 1u) & 1u);
             if (d.sid != kK1EndOfWork) {
                 const uint32_t vt = d.v0 + d.t0;
-                if (warp < static_cast<uint32_t>(kK1Levels))
+                if (kK1Lpw > 1 || kK1Grouped)
+                    disorder |= k1_build_tile<kSafe>(warp, heads, links, runs, W, d);
+                else if (warp < static_cast<uint32_t>(kK1Levels))
                     disorder |= k1_build_level<kSafe>(heads + warp * kK1Slots, links + warp * kK1LinkRing, W, vt,
                                                       d.tile_n, m0, m1, m2);
                 else
