@@ -77,6 +77,7 @@ def cpu_roundtrip(codec, raw, n_chunks, chunk, threads):
     c_len, t_c = codec.run_streams(False, raw, in_off, in_len, comp, c_off, c_cap, threads)
     d_len, t_d = codec.run_streams(True, comp, c_off, c_len, dec, in_off, in_len, threads)
     assert (d_len == in_len).all() and (dec[:n_chunks * chunk] == raw[:n_chunks * chunk]).all()
+    cpu_roundtrip.last = (comp, c_off, c_len)           # for the parity check of the measured run
     return t_c, t_d, int(c_len.sum())
 
 
@@ -122,11 +123,16 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config():
-    return {"workload": "1 GiB synthetic mixed corpus (text / binary records / incompressible by chunk) per GPU, "
-                        "split into 64 KiB independent LZS streams; compress then decompress (BASELINE configs[1])",
-            "chunk_bytes": CHUNK, "bytes_per_gpu": 1 << 30, "seed": SEED,
-            "l2_policy": "inputs (1 GiB) larger than L2 (126 MB); no flush needed",
+def workload_config(bytes_per_gpu=1 << 30, total_gib=None):
+    if total_gib:
+        what = ("%d GiB synthetic mixed corpus (text / binary records / incompressible by chunk) sharded over the GPUs "
+                "in contiguous chunk ranges, 64 KiB independent LZS streams; compress then decompress "
+                "(BASELINE configs[3])" % total_gib)
+    else:
+        what = ("1 GiB synthetic mixed corpus (text / binary records / incompressible by chunk) per GPU, "
+                "split into 64 KiB independent LZS streams; compress then decompress (BASELINE configs[1])")
+    return {"workload": what, "chunk_bytes": CHUNK, "bytes_per_gpu": bytes_per_gpu, "seed": SEED,
+            "l2_policy": "inputs (>= 1 GiB per GPU) larger than L2 (126 MB); no flush needed",
             "parallelism": "independent chunk ranges per GPU, no data-path collective"}
 
 
@@ -196,6 +202,10 @@ def run_gpu_arm(args):
     B.lib()
 
     total = 1 << 30
+    if args.total_gib:
+        if (args.total_gib << 30) % (world * CHUNK):
+            raise SystemExit("bench.py: --total-gib must split into whole chunks per GPU")
+        total = (args.total_gib << 30) // world         # strong scaling: the corpus is fixed, the shards shrink
     n_chunks = total // CHUNK
     db = B.DeviceBatch(total, CHUNK, device=dev)
     db.fill(B.CORPUS_MIXED, SEED, first_index=rank * n_chunks)     # this rank's shard of the corpus
@@ -241,34 +251,53 @@ def run_gpu_arm(args):
     assert db.roundtrip_ok(), "round trip mismatch inside the timed region"
     comp_bytes = db.compressed_bytes()
 
-    # ---- optional exchange step (N > 1): all-gather-v of the variable-size outputs over NCCL,
-    #      timed separately -- it is not part of the data path
+    # ---- the exchange step (N > 1): all-gather-v of the variable-size outputs over NCCL, timed on
+    #      the device.  It is not part of the data path, so `value` excludes
+    #      it and `value_with_gather` includes it.
     gather = None
     if dist is not None:
         import lzs_dist
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for it in range(2):
+        g = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        best = None
+        for it in range(3):
             barrier()
-            g0.record()
-            packed = lzs_dist.pack_streams(db.comp, db.comp_off, db.comp_len)
+            g[0].record()
+            packed, _ = lzs_dist.pack_streams(db.comp, db.comp_off, db.comp_len)
+            g[1].record()
             payload, lens, offs = lzs_dist.all_gather_streams(packed, db.comp_len)
-            g1.record()
+            g[2].record()
             torch.cuda.synchronize()
-        gather = {"ms": g0.elapsed_time(g1), "bytes_per_rank_received": int(payload.numel()),
-                  "streams": int(lens.numel()), "what": "pack + all-gather-v of compressed streams to every rank (NCCL)"}
-        assert int(lens.numel()) == n_chunks * world and int(payload.numel()) == int(lens.sum().item())
+            t = (g[0].elapsed_time(g[2]), g[0].elapsed_time(g[1]), g[1].elapsed_time(g[2]))
+            if it and (best is None or t[0] < best[0]):
+                best = t
+        assert int(lens.numel()) == n_chunks * world
+        # every rank holds every stream: check this rank's own streams, and one from each peer by its end marker
+        mine = slice(rank * n_chunks, (rank + 1) * n_chunks)
+        assert torch.equal(lens[mine], db.comp_len.to(torch.int64))
+        probe = int(offs[mine][n_chunks // 2])
+        own_off = int(db.comp_off[n_chunks // 2])
+        ln = int(db.comp_len[n_chunks // 2])
+        assert torch.equal(payload[probe:probe + ln], db.comp[own_off:own_off + ln]), "gathered stream differs"
+        recv = int(payload.numel()) - int(packed.numel())
+        gather = {"ms": best[0], "pack_ms": best[1], "exchange_ms": best[2],
+                  "bytes_per_rank_received": recv, "payload_bytes": int(payload.numel()), "streams": int(lens.numel()),
+                  "bus_gbs_per_rank_in": recv / (best[2] * 1e-3) / 1e9 if best[2] > 0 else None,
+                  "what": "device pack kernel + all-gather-v (exact sizes, grouped NCCL send/recv into place) "
+                          "of all compressed streams to every rank; best of 2 after a warm-up"}
 
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(B, db, total, n_chunks, max(1, min(args.steps, 3)), barrier)
 
-    stats = torch.tensor([t_total, t_k1, t_k23, t_k4, e2e["ms"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    stats = torch.tensor([t_total, t_k1, t_k23, t_k4, e2e["ms"] if e2e else 0.0, gather["ms"] if gather else 0.0,
+                          e2e["copy_only_ms"] if e2e else 0.0, e2e["pageable_ms"] if e2e and e2e.get("pageable_ms") else 0.0],
+                         dtype=torch.float64, device=dev)
     sums = torch.tensor([float(comp_bytes)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    t_total, t_k1, t_k23, t_k4, t_e2e = [float(x) for x in stats.tolist()]
+    t_total, t_k1, t_k23, t_k4, t_e2e, t_gather, t_copy, t_pageable = [float(x) for x in stats.tolist()]
     comp_all = float(sums.item())
 
     if rank == 0:
@@ -287,8 +316,8 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": job_bytes / (t_total * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(),
+            "scaling": "strong" if args.total_gib else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(total, args.total_gib),
             "compress_gbs": job_bytes / ((t_k1 + t_k23) * 1e-3) / 1e9,
             "decompress_gbs": job_bytes / (t_k4 * 1e-3) / 1e9,
             "ratio": job_bytes / comp_all,
@@ -297,11 +326,23 @@ def run_gpu_arm(args):
         if e2e:
             line["e2e"] = {"value": job_bytes / (t_e2e * 1e-3) / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "steps": e2e["steps"], "api": "lzs_b200_compress_packed_host + lzs_b200_decompress_batch_host"}
+                           "steps": e2e["steps"], "api": "lzs_b200_compress_packed_host + lzs_b200_decompress_batch_host",
+                           "host_buffers": "pinned",
+                           # the same bytes over PCIe in the same order with no kernel at all: the ceiling of this box
+                           "copy_only": {"value": job_bytes / (t_copy * 1e-3) / 1e9, "unit": "GB/s", "ms": t_copy,
+                                         "what": "H2D input, D2H packed streams, then H2D packed streams, D2H output; "
+                                                 "pinned, two copy engines, max over ranks"},
+                           "frac_of_copy_ceiling": t_copy / t_e2e if t_e2e > 0 else None}
+            if t_pageable > 0:
+                line["e2e"]["pageable"] = {"value": job_bytes / (t_pageable * 1e-3) / 1e9, "unit": "GB/s",
+                                           "what": "the same calls on plain malloc'ed (pageable) caller buffers"}
         if gather:
+            gather["ms"] = t_gather
             line["gather"] = gather
+            line["value_with_gather"] = job_bytes / ((t_total + t_gather) * 1e-3) / 1e9
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_leg(db)
+            line["parity"] = line["cpu_baseline"].pop("parity")
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -349,10 +390,60 @@ def run_e2e(B, db, total, n_chunks, steps, barrier):
     ms = (time.perf_counter() - t0) * 1e3 / steps
     assert torch.equal(dec[:total], raw[:total]), "e2e round trip mismatch"
     packed = int(used[0])
+
+    # ---- the same bytes over PCIe with no kernels (what this box's copy engines can do at best)
+    d_a = db.dec                      # any device buffers of the right size: contents do not matter
+    d_b = db.comp
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_only():
+        with torch.cuda.stream(s_up):
+            d_a[:total].copy_(raw[:total], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            comp[:packed].copy_(d_b[:packed], non_blocking=True)
+        torch.cuda.synchronize()       # the compress call returns before the decompress call starts
+        with torch.cuda.stream(s_up):
+            d_b[:packed].copy_(comp[:packed], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            dec[:total].copy_(d_a[:total], non_blocking=True)
+        torch.cuda.synchronize()
+
+    copy_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        copy_only()
+    barrier()
+    copy_ms = (time.perf_counter() - t0) * 1e3 / steps
+
+    # ---- the same calls on pageable caller memory (what a plain lzs.h-style caller passes)
+    pageable_ms = None
+    if not getattr(run_e2e, "skip_pageable", False):
+        raw_p = np.empty(total + 64, dtype=np.uint8)
+        raw_p[:total] = raw[:total].numpy()
+        comp_p = np.empty(n_chunks * stride + 64, dtype=np.uint8)
+        dec_p = np.empty(total + 64, dtype=np.uint8)
+
+        def step_pageable():
+            B.check(L.lzs_b200_compress_packed_host(B._p(raw_p), B._p(in_off, u64), B._p(in_len, u32), total,
+                                                    B._p(comp_p), n_chunks * stride, B._p(c_offp, u64), B._p(c_len, u32),
+                                                    n_chunks, B._p(used, u64)))
+            B.check(L.lzs_b200_decompress_batch_host(B._p(comp_p), B._p(c_offp, u64), B._p(c_len, u32), int(used[0]),
+                                                     B._p(dec_p), B._p(in_off, u64), B._p(in_len, u32), B._p(d_len, u32),
+                                                     total, n_chunks))
+
+        step_pageable()
+        barrier()
+        t0 = time.perf_counter()
+        step_pageable()
+        barrier()
+        pageable_ms = (time.perf_counter() - t0) * 1e3
+        assert (dec_p[:total] == raw_p[:total]).all(), "e2e (pageable) round trip mismatch"
     arrays = n_chunks * 24
     h2d = total + arrays + 8 * n_chunks + packed + arrays  # compress input (+ tables), decompress input = packed streams
     d2h = packed + 4 * n_chunks + total + 4 * n_chunks
-    return {"ms": ms, "h2d": int(h2d), "d2h": int(d2h), "steps": steps}
+    return {"ms": ms, "h2d": int(h2d), "d2h": int(d2h), "steps": steps, "copy_only_ms": copy_ms,
+            "pageable_ms": pageable_ms}
 
 
 def cpu_baseline_leg(db):
@@ -364,9 +455,24 @@ def cpu_baseline_leg(db):
     raw[:n * CHUNK] = db.raw[:n * CHUNK].cpu().numpy()
     cpu_roundtrip(codec, raw, min(n, 256), CHUNK, threads)                     # warm
     t_c, t_d, comp_bytes = cpu_roundtrip(codec, raw, n, CHUNK, threads)
+    # parity inside the measured run: the streams the timed GPU steps left in HBM for these chunks
+    # against the CPU codec's streams for the same bytes -- lengths and every byte
+    cpu_comp, cpu_off, cpu_len = cpu_roundtrip.last
+    gpu_len = db.comp_len[:n].cpu().numpy().astype(np.uint32)
+    gpu_comp = db.comp[:n * db.comp_stride].cpu().numpy()
+    mismatches = 0
+    for s in range(n):
+        a, b = int(cpu_off[s]), s * db.comp_stride
+        if gpu_len[s] != cpu_len[s] or not np.array_equal(cpu_comp[a:a + int(cpu_len[s])], gpu_comp[b:b + int(gpu_len[s])]):
+            mismatches += 1
+    parity = {"streams": n, "mismatches": mismatches, "against": kind,
+              "what": "compressed streams of the timed run (first %d chunks) byte-compared with the CPU codec's; "
+                      "the full round trip of all chunks is asserted on the device" % n}
+    if mismatches:
+        raise SystemExit("bench.py: %d of %d GPU streams differ from the CPU %s" % (mismatches, n, kind))
     t1_c, t1_d, _ = cpu_roundtrip(codec, raw, 128, CHUNK, 1)
     nbytes = n * CHUNK
-    return {"value": nbytes / (t_c + t_d) / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+    return {"parity": parity, "value": nbytes / (t_c + t_d) / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
             "sample": "first %d chunks (%d MiB) of the timed corpus, one pass, all host threads" % (n, nbytes >> 20),
             "compress_gbs": nbytes / t_c / 1e9, "decompress_gbs": nbytes / t_d / 1e9, "ratio": nbytes / comp_bytes,
             "single_thread": {"compress_gbs": 128 * CHUNK / t1_c / 1e9, "decompress_gbs": 128 * CHUNK / t1_d / 1e9,
@@ -381,7 +487,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--total-gib", type=int, default=0,
+                    help="BASELINE configs[3]: one corpus of this many GiB sharded over the GPUs (default: 1 GiB per GPU)")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory end-to-end figure")
     args = ap.parse_args()
+    run_e2e.skip_pageable = args.no_pageable
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

@@ -77,6 +77,13 @@ int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *i
                                             uint32_t *out_len, uint8_t *status, uint32_t n_streams,
                                             void *scratch, size_t scratch_bytes, void *stream);
 
+/* Copies n streams from their slots (src + src_off[s], len[s] bytes) to packed positions
+ * (dst + dst_off[s]); both offsets must be multiples of 16 and every slot readable up to the
+ * next multiple of 16 of its length.  What the packed host compressor and the multi-GPU gather
+ * of variable-size outputs use to put streams back to back. */
+int lzs_b200_pack_streams_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint8_t *dst,
+                                 const uint64_t *dst_off, uint32_t n_streams, void *stream);
+
 /* Individual stages of the compressor, for tests and profiling:
  * K1 writes one record per input byte, (len << 11) | offset with len 0 or 2..12;
  * K2+K3 turn records + input into streams.  `counter` is device scratch of at least 16 bytes
@@ -92,7 +99,12 @@ int lzs_b200_parse_pack_batch_device(const uint8_t *in, const uint64_t *in_off, 
  * Host-resident batches: same meaning, HOST pointers, synchronous.  Input is
  * copied to the device, processed and copied back inside the call (pinned host
  * memory makes the copies faster but is not required).  in_span / out_span are the
- * number of bytes of `in` / `out` covered by the batch.
+ * number of bytes of `in` / `out` covered by the batch; a stream or slot that reaches
+ * beyond them is refused (LZS_B200_EINVAL), nothing is processed.
+ * What the call writes to `out`: the out_len[s] bytes of every stream.  The rest of a
+ * slot, [out_off[s] + out_len[s], out_off[s] + out_cap[s]), is unspecified afterwards;
+ * bytes outside every slot (framing the caller keeps between slots) are never touched.
+ * The calls keep grow-only device buffers between calls; lzs_b200_release() frees them.
  * ---------------------------------------------------------------------------- */
 int lzs_b200_compress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                                  uint64_t in_span, uint8_t *out, const uint64_t *out_off,
@@ -140,8 +152,17 @@ void     lzs_b200_chunk_layout(uint64_t total, uint32_t chunk, uint64_t out_stri
 int lzs_b200_corpus_fill_device(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
                                 uint64_t n, uint64_t seed, int kind, void *stream);
 
+/* Frees the device and pinned buffers the host-pointer entry points (and the lzs.h drop-in
+ * calls, which sit on them) keep between calls on the current device.  Safe at any time
+ * between calls; the next call allocates again. */
+int lzs_b200_release(void);
+
 /* Tuning knobs (also read once from the environment: LZS_B200_DECODE_LANES). */
 int lzs_b200_set_decode_lanes(int lanes_per_stream);   /* 4, 8, 16 or 32 */
+/* Test knob: run the match finder's exact-for-any-exchange-order launch after every fast launch
+ * (normally it returns at once: sm_100a serves the exchanges in the order the fast launch
+ * assumes).  Same records, several times slower. */
+int lzs_b200_set_force_safe_match(int on);
 
 /* Number of kernels launched by this library in the calling process so far. */
 uint64_t lzs_b200_kernel_launches(void);

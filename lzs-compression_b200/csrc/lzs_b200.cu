@@ -29,6 +29,7 @@ namespace {
 thread_local char          g_err[512] = "";
 std::atomic<uint64_t>      g_launches{0};
 std::atomic<int>           g_decode_lanes{0};
+std::atomic<int>           g_force_safe_match{0};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -150,6 +151,12 @@ int lzs_b200_set_decode_lanes(int lanes)
     return LZS_B200_OK;
 }
 
+int lzs_b200_set_force_safe_match(int on)
+{
+    g_force_safe_match.store(on ? 1 : 0);
+    return LZS_B200_OK;
+}
+
 size_t lzs_b200_compress_scratch_bytes(uint64_t in_span)
 {
     return kCounterBytes + align_up(static_cast<size_t>(in_span) * sizeof(lzs::match_t) + 64, 256);
@@ -167,6 +174,9 @@ int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), st));
+    /* test knob: pretend the fast launch saw an exchange order it does not handle, so that the
+     * exact-for-any-order launch really runs (and overwrites every record) on this hardware */
+    if (g_force_safe_match.load()) CUDA_TRY(cudaMemsetAsync(counter + 2, 1, 1, st));
     const unsigned grid = n_streams < static_cast<uint32_t>(d->sms) ? n_streams : static_cast<unsigned>(d->sms);
     lzs::k1_match<false><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
                                                                           counter);
@@ -280,6 +290,18 @@ int lzs_b200_corpus_fill_device(uint8_t *dst, uint64_t stride, uint32_t stream_l
     return LZS_B200_OK;
 }
 
+int lzs_b200_pack_streams_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint8_t *dst,
+                                 const uint64_t *dst_off, uint32_t n_streams, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!src || !src_off || !len || !dst || !dst_off) return fail(LZS_B200_EINVAL, "null pointer");
+    gather_streams_kernel<<<n_streams, 128, 0, static_cast<cudaStream_t>(stream)>>>(src, src_off, len, dst, dst_off,
+                                                                                    n_streams);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
 uint32_t lzs_b200_chunk_count(uint64_t total, uint32_t chunk)
 {
     if (chunk == 0) return 0;
@@ -319,7 +341,9 @@ __global__ void publish_lengths_kernel(uint32_t *__restrict__ host_mapped, const
 }
 
 struct HostPath {
-    std::mutex   mu;
+    std::mutex     mu;
+    std::once_flag once;                    /* streams are created once per device        */
+    int            init_rc = LZS_B200_OK;
     cudaStream_t stream = nullptr;          /* copies of small arrays, simple path        */
     cudaStream_t work[8] = {};              /* slice k: upload + kernels on work[k % 8]   */
     cudaStream_t down = nullptr;            /* downloads of finished slices               */
@@ -329,6 +353,38 @@ struct HostPath {
     uint32_t    *pinned_len = nullptr;      /* pinned, device-mapped: per-stream result lengths */
     uint32_t    *pinned_len_dev = nullptr;  /* the same memory as the device addresses it       */
     size_t       pinned_cap = 0;
+    uint8_t     *bounce = nullptr;          /* pinned staging for outputs whose slots have gaps */
+    size_t       bounce_cap = 0;
+
+    int reserve_bounce(size_t bytes)
+    {
+        if (bounce_cap >= bytes) return LZS_B200_OK;
+        if (bounce) cudaFreeHost(bounce);
+        bounce = nullptr;
+        bounce_cap = 0;
+        if (cudaHostAlloc(reinterpret_cast<void **>(&bounce), bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LZS_B200_ENOMEM, "cudaHostAlloc(%zu) failed", bytes);
+        }
+        bounce_cap = bytes;
+        return LZS_B200_OK;
+    }
+
+    /* give the device and pinned memory back (the streams stay) */
+    void release()
+    {
+        for (int i = 0; i < 11; i++) {
+            if (buf[i]) cudaFree(buf[i]);
+            buf[i] = nullptr;
+            cap[i] = 0;
+        }
+        if (pinned_len) cudaFreeHost(pinned_len);
+        pinned_len = pinned_len_dev = nullptr;
+        pinned_cap = 0;
+        if (bounce) cudaFreeHost(bounce);
+        bounce = nullptr;
+        bounce_cap = 0;
+    }
 
     int reserve_pinned(size_t count)
     {
@@ -363,32 +419,131 @@ struct HostPath {
     }
 };
 
-int host_path(HostPath **out)
+HostPath *host_path_slot(int *rc_out)
 {
     static HostPath paths[64];
     int             dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(LZS_B200_EINVAL, "device ordinal %d out of range", dev);
-    HostPath &p = paths[dev];
-    if (!p.stream) {
-        std::lock_guard<std::mutex> lock(p.mu);
-        if (!p.stream) {
-            /* Priorities fall from work[0] to work[7]: the decoder's slices run concurrently (it
-             * takes several to fill the GPU), and the earlier slice should win the SMs so that its
-             * download can start while the later ones are still being decoded.  `down` also runs
-             * the small gather kernel of the packed compressor: highest priority as well. */
-            int prio_lo = 0, prio_hi = 0;           /* numerically lower = more urgent */
-            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-            for (int i = 0; i < 8; i++) {
-                const int pr = prio_hi + i < prio_lo ? prio_hi + i : prio_lo;
-                CUDA_TRY(cudaStreamCreateWithPriority(&p.work[i], cudaStreamNonBlocking, pr));
-            }
-            CUDA_TRY(cudaStreamCreateWithPriority(&p.down, cudaStreamNonBlocking, prio_hi));
-            CUDA_TRY(cudaStreamCreateWithFlags(&p.up, cudaStreamNonBlocking));
-            CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
-        }
+    cudaError_t     e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        *rc_out = fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? LZS_B200_ENODEVICE : LZS_B200_ECUDA,
+                       "cudaGetDevice failed: %s", cudaGetErrorString(e));
+        return nullptr;
     }
-    *out = &p;
+    if (dev < 0 || dev >= 64) {
+        *rc_out = fail(LZS_B200_EINVAL, "device ordinal %d out of range", dev);
+        return nullptr;
+    }
+    *rc_out = LZS_B200_OK;
+    return &paths[dev];
+}
+
+int host_path_init(HostPath &p)
+{
+    /* Priorities fall from work[0] to work[7]: the decoder's slices run concurrently (it
+     * takes several to fill the GPU), and the earlier slice should win the SMs so that its
+     * download can start while the later ones are still being decoded.  `down` also runs
+     * the small gather kernel of the packed compressor: highest priority as well. */
+    int prio_lo = 0, prio_hi = 0;           /* numerically lower = more urgent */
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = 0; i < 8; i++) {
+        const int pr = prio_hi + i < prio_lo ? prio_hi + i : prio_lo;
+        CUDA_TRY(cudaStreamCreateWithPriority(&p.work[i], cudaStreamNonBlocking, pr));
+    }
+    CUDA_TRY(cudaStreamCreateWithPriority(&p.down, cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.up, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+    return LZS_B200_OK;
+}
+
+int host_path(HostPath **out)
+{
+    int       rc = LZS_B200_OK;
+    HostPath *p = host_path_slot(&rc);
+    if (!p) return rc;
+    std::call_once(p->once, [p] { p->init_rc = host_path_init(*p); });
+    if (p->init_rc) return fail(p->init_rc, "creating the CUDA streams of the host path failed");
+    *out = p;
+    return LZS_B200_OK;
+}
+
+/* Everything the sliced pipelines create per call; the destructor runs on EVERY exit, so an
+ * error in the middle of a pipeline leaves no copy in flight on the caller's buffers, no kernel
+ * on the arena the next call will reuse, and no event behind. */
+struct PipelineScope {
+    HostPath                &p;
+    std::vector<cudaEvent_t> events;
+    explicit PipelineScope(HostPath &hp) : p(hp) {}
+    int make(cudaEvent_t *e, unsigned flags)
+    {
+        CUDA_TRY(cudaEventCreateWithFlags(e, flags));
+        events.push_back(*e);
+        return LZS_B200_OK;
+    }
+    cudaError_t drain()
+    {
+        cudaError_t first = cudaSuccess;
+        auto note = [&](cudaError_t e) { if (e != cudaSuccess && first == cudaSuccess) first = e; };
+        for (auto &w : p.work) note(cudaStreamSynchronize(w));
+        note(cudaStreamSynchronize(p.down));
+        note(cudaStreamSynchronize(p.up));
+        note(cudaStreamSynchronize(p.stream));
+        return first;
+    }
+    ~PipelineScope()
+    {
+        drain();
+        for (auto &e : events) cudaEventDestroy(e);
+        cudaGetLastError();
+    }
+};
+
+/* The caller's description of a batch must stay inside the spans it states: the device arena
+ * is sized from the spans, and a slot that reaches beyond them would be written outside it. */
+int check_layout(const uint64_t *in_off, const uint32_t *in_len, uint64_t in_span, const uint64_t *out_off,
+                 const uint32_t *out_cap, uint64_t out_span, uint32_t n)
+{
+    for (uint32_t s = 0; s < n; s++) {
+        if (in_off[s] > in_span || in_len[s] > in_span - in_off[s])
+            return fail(LZS_B200_EINVAL, "stream %u: input [%llu, +%u) reaches beyond in_span %llu", s,
+                        static_cast<unsigned long long>(in_off[s]), in_len[s], static_cast<unsigned long long>(in_span));
+        if (out_off && (out_off[s] > out_span || out_cap[s] > out_span - out_off[s]))
+            return fail(LZS_B200_EINVAL, "stream %u: output slot [%llu, +%u) reaches beyond out_span %llu", s,
+                        static_cast<unsigned long long>(out_off[s]), out_cap[s], static_cast<unsigned long long>(out_span));
+    }
+    return LZS_B200_OK;
+}
+
+/* Bring the bytes streams [a, b) produced back to the caller: only [out_off, out_off + out_len)
+ * of a stream, never a byte outside the slots (the caller may keep framing between them).
+ * Slots that touch are fetched in one copy up to the last produced byte (what lies between two
+ * produced streams is then slot space, which the contract leaves unspecified); a slice whose
+ * slots have gaps everywhere goes through a pinned staging buffer and host copies instead of
+ * thousands of small device copies. */
+int download_streams(HostPath &p, uint8_t *out, const uint8_t *d_out, const uint64_t *out_off, const uint32_t *out_cap,
+                     const uint32_t *out_len, uint32_t a, uint32_t b, cudaStream_t st, bool *used_bounce)
+{
+    struct Run { uint64_t lo, hi; };
+    std::vector<Run> runs;
+    uint64_t         slot_end = 0;
+    for (uint32_t s = a; s < b; s++) {
+        if (out_len[s] == 0) continue;
+        const uint64_t lo = out_off[s], hi = out_off[s] + out_len[s];
+        if (!runs.empty() && lo == slot_end) runs.back().hi = hi;     /* touches the previous slot */
+        else runs.push_back({lo, hi});
+        slot_end = out_off[s] + out_cap[s];
+    }
+    if (runs.size() <= 64) {
+        for (const Run &r : runs)
+            CUDA_TRY(cudaMemcpyAsync(out + r.lo, d_out + r.lo, r.hi - r.lo, cudaMemcpyDeviceToHost, st));
+        return LZS_B200_OK;
+    }
+    const uint64_t lo = runs.front().lo, hi = runs.back().hi;
+    int            rc = p.reserve_bounce(hi - lo);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(p.bounce, d_out + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (const Run &r : runs) memcpy(out + r.lo, p.bounce + (r.lo - lo), r.hi - r.lo);
+    if (used_bounce) *used_bounce = true;
     return LZS_B200_OK;
 }
 
@@ -480,14 +635,16 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     if (n == 0) return LZS_B200_OK;
     if (!in_off || !in_len || !out_off || !out_cap || !out_len || (!in && in_span) || (!out && out_span))
         return fail(LZS_B200_EINVAL, "null pointer");
+    int rc = check_layout(in_off, in_len, in_span, out_off, out_cap, out_span, n);
+    if (rc) return rc;
     if (lzs_b200_device_count() <= 0) return fail(LZS_B200_ENODEVICE, "no CUDA device: the LZS codec has no CPU path");
     HostPath *hp = nullptr;
-    int       rc = host_path(&hp);
-    if (rc) return rc;
+    if ((rc = host_path(&hp))) return rc;
     std::lock_guard<std::mutex> lock(hp->mu);
-    HostPath    &p = *hp;
-    cudaStream_t st = p.stream;
-    const size_t scratch = decompress ? lzs_b200_decompress_scratch_bytes() : lzs_b200_compress_scratch_bytes(in_span);
+    HostPath     &p = *hp;
+    PipelineScope scope(p);                 /* declared after the lock: drains before the arena is released */
+    cudaStream_t  st = p.stream;
+    const size_t  scratch = decompress ? lzs_b200_decompress_scratch_bytes() : lzs_b200_compress_scratch_bytes(in_span);
     if ((rc = p.reserve(S_IN, in_span + 64))) return rc;
     if ((rc = p.reserve(S_OUT, out_span + 64))) return rc;
     if ((rc = p.reserve(S_INOFF, n * sizeof(uint64_t)))) return rc;
@@ -497,13 +654,23 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     if ((rc = p.reserve(S_OUTLEN, n * sizeof(uint32_t)))) return rc;
     if ((rc = p.reserve(S_SCRATCH, scratch))) return rc;
 
-    uint8_t *d_in = static_cast<uint8_t *>(p.buf[S_IN]);
-    uint8_t *d_out = static_cast<uint8_t *>(p.buf[S_OUT]);
+    uint8_t  *d_in = static_cast<uint8_t *>(p.buf[S_IN]);
+    uint8_t  *d_out = static_cast<uint8_t *>(p.buf[S_OUT]);
+    uint64_t *d_inoff = static_cast<uint64_t *>(p.buf[S_INOFF]);
+    uint32_t *d_inlen = static_cast<uint32_t *>(p.buf[S_INLEN]);
+    uint64_t *d_outoff = static_cast<uint64_t *>(p.buf[S_OUTOFF]);
+    uint32_t *d_outcap = static_cast<uint32_t *>(p.buf[S_OUTCAP]);
+    uint32_t *d_outlen = static_cast<uint32_t *>(p.buf[S_OUTLEN]);
+    CUDA_TRY(cudaMemcpyAsync(d_inoff, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_inlen, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_outoff, out_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_outcap, out_cap, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     /* Streams laid out in increasing order (the usual chunked file / packet table) are
      * processed in slices so that upload, kernels and download of different slices
      * overlap: slice k uploads and computes on work[k % 8] (the decoder needs several
-     * slices resident at once to fill the GPU), finished slices are downloaded on `down`, and only the bytes a slice really produced come back. */
+     * slices resident at once to fill the GPU), finished slices are downloaded on `down`, and
+     * only the bytes a slice really produced come back. */
     bool ordered = n > 8;
     for (uint32_t s2 = 1; s2 < n && ordered; s2++)
         ordered = in_off[s2] >= in_off[s2 - 1] + in_len[s2 - 1] && out_off[s2] >= out_off[s2 - 1] + out_cap[s2 - 1];
@@ -515,18 +682,9 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
         if ((rc = p.reserve(S_COUNTERS, static_cast<size_t>(nslice) * 512))) return rc;
         if ((rc = p.reserve_pinned(n))) return rc;          /* D2H into pageable memory would block the host */
         uint8_t *d_cnt = static_cast<uint8_t *>(p.buf[S_COUNTERS]);
-        uint64_t *d_inoff = static_cast<uint64_t *>(p.buf[S_INOFF]);
-        uint32_t *d_inlen = static_cast<uint32_t *>(p.buf[S_INLEN]);
-        uint64_t *d_outoff = static_cast<uint64_t *>(p.buf[S_OUTOFF]);
-        uint32_t *d_outcap = static_cast<uint32_t *>(p.buf[S_OUTCAP]);
-        uint32_t *d_outlen = static_cast<uint32_t *>(p.buf[S_OUTLEN]);
-        CUDA_TRY(cudaMemcpyAsync(d_inoff, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_inlen, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_outoff, out_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_outcap, out_cap, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         std::vector<cudaEvent_t> ev(nslice + 1), up_ev(nslice);
-        for (auto &e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto &e : up_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : ev) if ((rc = scope.make(&e, cudaEventDisableTiming))) return rc;
+        for (auto &e : up_ev) if ((rc = scope.make(&e, cudaEventDisableTiming))) return rc;
         CUDA_TRY(cudaEventRecord(ev[nslice], st));
         for (auto &w : p.work) CUDA_TRY(cudaStreamWaitEvent(w, ev[nslice], 0));
         CUDA_TRY(cudaStreamWaitEvent(p.up, ev[nslice], 0));
@@ -534,9 +692,9 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
         /* LZS_B200_TRACE=1 prints when every stage of every slice finished (ms from the start) */
         const bool               trace = getenv("LZS_B200_TRACE") != nullptr;
         std::vector<cudaEvent_t> tr(trace ? nslice * 4 + 1 : 0);
-        for (auto &e : tr) CUDA_TRY(cudaEventCreate(&e));
+        for (auto &e : tr) if ((rc = scope.make(&e, cudaEventDefault))) return rc;
         if (trace) cudaEventRecord(tr[nslice * 4], st);
-        for (uint32_t k = 0; k < nslice && !rc; k++) {
+        for (uint32_t k = 0; k < nslice; k++) {
             const uint32_t a = first[k], b = first[k + 1], cnt = b - a;
             /* The decoder runs slice k on work[k % 8]: it needs several slices resident at once to
              * fill the GPU.  The compressor's match finder fills the GPU with any slice, so its
@@ -566,27 +724,22 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
                     rc = lzs_b200_parse_pack_batch_device(d_in, d_inoff + a, d_inlen + a, matches, d_out, d_outoff + a,
                                                           d_outcap + a, d_outlen + a, cnt, ws);
             }
-            if (rc) break;
+            if (rc) return rc;
             if (trace) cudaEventRecord(tr[k * 4 + 1], ws);
             publish_lengths_kernel<<<(cnt + 255u) / 256u, 256, 0, ws>>>(p.pinned_len_dev + a, d_outlen + a, cnt);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(ev[k], ws));
         }
-        for (uint32_t k = 0; k < nslice && !rc; k++) {
+        for (uint32_t k = 0; k < nslice; k++) {
             const uint32_t a = first[k], b = first[k + 1];
             CUDA_TRY(cudaEventSynchronize(ev[k]));
             memcpy(out_len + a, p.pinned_len + a, (b - a) * sizeof(uint32_t));
-            uint64_t top = 0;
-            for (uint32_t s2 = a; s2 < b; s2++)
-                if (out_len[s2] && out_off[s2] + out_len[s2] > top) top = out_off[s2] + out_len[s2];
             if (trace) cudaEventRecord(tr[k * 4 + 2], p.down);
-            if (top > out_off[a])
-                CUDA_TRY(cudaMemcpyAsync(out + out_off[a], d_out + out_off[a], top - out_off[a], cudaMemcpyDeviceToHost,
-                                         p.down));
+            if ((rc = download_streams(p, out, d_out, out_off, out_cap, out_len, a, b, p.down, nullptr))) return rc;
             if (trace) cudaEventRecord(tr[k * 4 + 3], p.down);
         }
-        if (trace && !rc) {
-            cudaDeviceSynchronize();
+        CUDA_TRY(scope.drain());
+        if (trace) {
             for (uint32_t k = 0; k < nslice; k++) {
                 float t[4] = {0, 0, 0, 0};
                 for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tr[nslice * 4], tr[k * 4 + j]);
@@ -594,58 +747,21 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
                         decompress ? "decompress" : "compress", k, first[k + 1] - first[k], t[0], t[1], t[2], t[3]);
             }
         }
-        for (auto &e : tr) cudaEventDestroy(e);
-        cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-        for (auto &w : p.work) {
-            cudaError_t e = cudaStreamSynchronize(w);
-            if (e != cudaSuccess) e1 = e;
-        }
-        cudaError_t e3 = cudaStreamSynchronize(p.down);
-        cudaStreamSynchronize(p.up);                        /* nothing may still read the caller's buffer */
-        for (auto &e : ev) cudaEventDestroy(e);
-        for (auto &e : up_ev) cudaEventDestroy(e);
-        if (rc) return rc;
-        CUDA_TRY(e1);
-        CUDA_TRY(e2);
-        CUDA_TRY(e3);
         return LZS_B200_OK;
     }
 
     if (in_span) CUDA_TRY(cudaMemcpyAsync(d_in, in, in_span, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p.buf[S_INOFF], in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p.buf[S_INLEN], in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p.buf[S_OUTOFF], out_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p.buf[S_OUTCAP], out_cap, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     if (decompress)
-        rc = lzs_b200_decompress_batch_device(d_in, static_cast<uint64_t *>(p.buf[S_INOFF]),
-                                              static_cast<uint32_t *>(p.buf[S_INLEN]), d_out,
-                                              static_cast<uint64_t *>(p.buf[S_OUTOFF]),
-                                              static_cast<uint32_t *>(p.buf[S_OUTCAP]),
-                                              static_cast<uint32_t *>(p.buf[S_OUTLEN]), n, p.buf[S_SCRATCH],
-                                              p.cap[S_SCRATCH], st);
+        rc = lzs_b200_decompress_batch_device(d_in, d_inoff, d_inlen, d_out, d_outoff, d_outcap, d_outlen, n,
+                                              p.buf[S_SCRATCH], p.cap[S_SCRATCH], st);
     else
-        rc = lzs_b200_compress_batch_device(d_in, static_cast<uint64_t *>(p.buf[S_INOFF]),
-                                            static_cast<uint32_t *>(p.buf[S_INLEN]), in_span, d_out,
-                                            static_cast<uint64_t *>(p.buf[S_OUTOFF]),
-                                            static_cast<uint32_t *>(p.buf[S_OUTCAP]),
-                                            static_cast<uint32_t *>(p.buf[S_OUTLEN]), n, p.buf[S_SCRATCH],
-                                            p.cap[S_SCRATCH], st);
+        rc = lzs_b200_compress_batch_device(d_in, d_inoff, d_inlen, in_span, d_out, d_outoff, d_outcap, d_outlen, n,
+                                            p.buf[S_SCRATCH], p.cap[S_SCRATCH], st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_len, p.buf[S_OUTLEN], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_len, d_outlen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    /* Copy back only what was produced.  Few streams: one copy each; many streams:
-     * one copy of the covered span (the gaps between slots are never read by callers). */
-    if (n <= 8) {
-        for (uint32_t s = 0; s < n; s++)
-            if (out_len[s])
-                CUDA_TRY(cudaMemcpyAsync(out + out_off[s], d_out + out_off[s], out_len[s],
-                                         cudaMemcpyDeviceToHost, st));
-    } else {
-        uint64_t hi = 0;
-        for (uint32_t s = 0; s < n; s++)
-            if (out_len[s] && out_off[s] + out_len[s] > hi) hi = out_off[s] + out_len[s];
-        if (hi) CUDA_TRY(cudaMemcpyAsync(out, d_out, hi, cudaMemcpyDeviceToHost, st));
-    }
+    /* only what was produced comes back, and nothing outside the slots is touched */
+    if ((rc = download_streams(p, out, d_out, out_off, out_cap, out_len, 0, n, st, nullptr))) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
     return LZS_B200_OK;
 }
@@ -664,13 +780,15 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
     for (uint32_t s2 = 1; s2 < n; s2++)
         if (in_off[s2] < in_off[s2 - 1] + in_len[s2 - 1])
             return fail(LZS_B200_EINVAL, "packed compression needs streams in increasing, non-overlapping order");
+    int rc = check_layout(in_off, in_len, in_span, nullptr, nullptr, 0, n);
+    if (rc) return rc;
     if (lzs_b200_device_count() <= 0) return fail(LZS_B200_ENODEVICE, "no CUDA device: the LZS codec has no CPU path");
     HostPath *hp = nullptr;
-    int       rc = host_path(&hp);
-    if (rc) return rc;
+    if ((rc = host_path(&hp))) return rc;
     std::lock_guard<std::mutex> lock(hp->mu);
-    HostPath    &p = *hp;
-    cudaStream_t st = p.stream;
+    HostPath     &p = *hp;
+    PipelineScope scope(p);
+    cudaStream_t  st = p.stream;
 
     /* internal slots: worst-case size of every stream, 16-byte aligned */
     std::vector<uint64_t> slot_off(n);
@@ -714,15 +832,15 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
     CUDA_TRY(cudaMemcpyAsync(d_slotoff, slot_off.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_slotcap, slot_cap.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     std::vector<cudaEvent_t> ev(nslice + 1), up_ev(nslice);
-    for (auto &e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto &e : up_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ev) if ((rc = scope.make(&e, cudaEventDisableTiming))) return rc;
+    for (auto &e : up_ev) if ((rc = scope.make(&e, cudaEventDisableTiming))) return rc;
     CUDA_TRY(cudaEventRecord(ev[nslice], st));
     for (auto &w : p.work) CUDA_TRY(cudaStreamWaitEvent(w, ev[nslice], 0));
     CUDA_TRY(cudaStreamWaitEvent(p.up, ev[nslice], 0));
     /* LZS_B200_TRACE=1 prints when every stage of every slice finished (ms from the start) */
     const bool               trace = getenv("LZS_B200_TRACE") != nullptr;
     std::vector<cudaEvent_t> tr(trace ? nslice * 6 + 1 : 0);
-    for (auto &e : tr) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : tr) if ((rc = scope.make(&e, cudaEventDefault))) return rc;
     auto mark = [&](uint32_t k, int j, cudaStream_t s2) { if (trace) cudaEventRecord(tr[k * 6 + j], s2); };
     if (trace) cudaEventRecord(tr[nslice * 6], st);
     for (uint32_t k = 0; k < nslice && !rc; k++) {
@@ -775,8 +893,9 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
             CUDA_TRY(cudaMemcpyAsync(out + begin, d_packed + begin, cursor - begin, cudaMemcpyDeviceToHost, p.down));
         mark(k, 5, p.down);
     }
-    if (trace && !rc) {
-        cudaDeviceSynchronize();
+    if (rc) return rc;
+    CUDA_TRY(scope.drain());
+    if (trace) {
         for (uint32_t k = 0; k < nslice; k++) {
             float t[6];
             for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], tr[nslice * 6], tr[k * 6 + j]);
@@ -784,19 +903,6 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
                     k, first[k + 1] - first[k], t[0], t[1], t[2], t[3], t[4], t[5]);
         }
     }
-    for (auto &e : tr) cudaEventDestroy(e);
-    cudaError_t e1 = cudaSuccess;
-    for (auto &w : p.work) {
-        cudaError_t e = cudaStreamSynchronize(w);
-        if (e != cudaSuccess) e1 = e;
-    }
-    cudaError_t e3 = cudaStreamSynchronize(p.down);
-    cudaStreamSynchronize(p.up);                            /* nothing may still read the caller's buffer */
-    for (auto &e : ev) cudaEventDestroy(e);
-    for (auto &e : up_ev) cudaEventDestroy(e);
-    if (rc) return rc;
-    CUDA_TRY(e1);
-    CUDA_TRY(e3);
     if (out_used) *out_used = cursor;
     return LZS_B200_OK;
 }
@@ -829,7 +935,25 @@ size_t single_call(bool decompress, uint8_t *out, size_t out_cap, const uint8_t 
 
 }  // namespace
 
+void lzs_b200_release_incremental_arena();
+
 extern "C" {
+
+/* The host-pointer entry points (and the drop-in lzs.h calls on top of them) keep grow-only
+ * device and pinned buffers per device between calls; this gives them back. */
+int lzs_b200_release(void)
+{
+    if (lzs_b200_device_count() <= 0) return LZS_B200_OK;
+    int       rc = LZS_B200_OK;
+    HostPath *p = host_path_slot(&rc);
+    if (!p) return rc;
+    {
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->release();
+    }
+    lzs_b200_release_incremental_arena();
+    return LZS_B200_OK;
+}
 
 int lzs_b200_compress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                                  uint64_t in_span, uint8_t *out, const uint64_t *out_off,

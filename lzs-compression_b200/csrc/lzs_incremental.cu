@@ -35,7 +35,8 @@ namespace {
 constexpr size_t kPieceMax = 1u << 30;          /* per device pass; larger slices are looped */
 
 struct Arena {
-    std::mutex   mu;
+    std::mutex     mu;
+    std::once_flag once;
     cudaStream_t stream = nullptr;
     void        *buf[4] = {};
     size_t       cap[4] = {};
@@ -58,17 +59,33 @@ Arena *arena()
     int          dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
     Arena &x = a[dev];
-    if (!x.stream) {
-        std::lock_guard<std::mutex> lock(x.mu);
-        if (!x.stream && cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    std::call_once(x.once, [&x] {
+        if (cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
-            return nullptr;
+            x.stream = nullptr;
         }
-    }
-    return &x;
+    });
+    return x.stream ? &x : nullptr;
 }
 
 enum { A_STATE, A_IN, A_OUT, A_JOBS };
+
+}  // namespace
+
+/* lzs_b200_release(): the incremental calls' share (lzs_b200.cu calls this) */
+void lzs_b200_release_incremental_arena()
+{
+    Arena *ap = arena();
+    if (!ap) return;
+    std::lock_guard<std::mutex> lock(ap->mu);
+    for (int i = 0; i < 4; i++) {
+        if (ap->buf[i]) cudaFree(ap->buf[i]);
+        ap->buf[i] = nullptr;
+        ap->cap[i] = 0;
+    }
+}
+
+namespace {
 
 struct View {                 /* the public members of any parameter block (lzs.h) */
     const uint8_t **in_ptr;

@@ -83,6 +83,8 @@ def lib():
     L.lzs_b200_corpus_fill_device.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
                                               ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp]
     L.lzs_b200_set_decode_lanes.argtypes = [ctypes.c_int]
+    L.lzs_b200_pack_streams_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
+    L.lzs_b200_release.restype = ctypes.c_int
     L.lzs_b200_chunk_count.restype = ctypes.c_uint32
     L.lzs_b200_chunk_count.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
     for name in ("lzs_compress", "lzs_simple_compress", "lzs_decompress"):

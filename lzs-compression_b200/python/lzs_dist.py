@@ -2,12 +2,21 @@
 
 Chunks / packets are independent streams, so the data path needs no collective: every
 rank compresses a contiguous range of stream indices on its own GPU.  The only exchange
-is the optional final gather of the variable-size outputs:
-all-gather the per-stream lengths, then all-gather the packed payloads padded to the
-largest rank (an all-gather-v).  Works on NCCL (CUDA tensors) and gloo (CPU tensors).
+is the optional final gather of the variable-size outputs, an
+all-gather-v:
+  1. every rank packs its streams back to back on the device (the library's pack kernel on
+     CUDA tensors: one block per stream, 16-byte vectors; a torch gather on CPU tensors);
+  2. one all-gather of (stream count, byte count) and one of the per-stream lengths;
+  3. the payloads travel with their EXACT sizes, every rank receiving each peer's payload
+     straight into its place in one preallocated buffer (grouped send/recv -- NCCL runs the
+     group as one operation over NVLink; nothing is padded to the largest rank and nothing
+     is concatenated afterwards).
+Works on NCCL (CUDA tensors) and gloo (CPU tensors; the multi-rank tests run that).
 """
 import torch
 import torch.distributed as dist
+
+ALIGN = 16
 
 
 def shard_range(n_streams, rank, world):
@@ -17,36 +26,78 @@ def shard_range(n_streams, rank, world):
     return lo, hi
 
 
-def pack_streams(buf, off, length):
-    """Concatenate buf[off[s] : off[s]+length[s]] for all s into one contiguous uint8 tensor."""
+def packed_layout(length, align=ALIGN):
+    """Offsets of streams put back to back, each starting at a multiple of `align`.
+    Returns (offsets int64, total bytes)."""
     length = length.to(torch.int64)
-    total = int(length.sum().item())
-    if total == 0:
-        return buf.new_empty(0)
-    start = torch.cumsum(length, 0) - length                      # exclusive prefix sum
-    idx = torch.repeat_interleave(off.to(torch.int64) - start, length) + torch.arange(total, device=buf.device)
-    return buf[idx]
+    padded = (length + (align - 1)) // align * align
+    off = torch.cumsum(padded, 0) - padded
+    total = int(padded.sum().item()) if length.numel() else 0
+    return off, total
 
 
-def all_gather_streams(packed, lengths, group=None):
-    """All-gather-v of packed payloads.  Returns (payload of all ranks in rank order,
-    lengths of all streams in rank order, byte offset of every stream in the payload)."""
+def pack_streams(buf, off, length, align=ALIGN):
+    """Streams buf[off[s] : off[s]+length[s]] put back to back (each at a multiple of `align`).
+    Returns (packed uint8 tensor, offsets into it).  CUDA tensors: the library's pack kernel on
+    the current stream; CPU tensors: plain slicing (small test sizes)."""
+    dst_off, total = packed_layout(length, align)
+    packed = torch.zeros(total, dtype=torch.uint8, device=buf.device)
+    n = int(length.numel())
+    if n == 0 or total == 0:
+        return packed, dst_off
+    if buf.is_cuda:
+        import lzs_b200 as B
+        src_off = off.to(torch.int64).contiguous()
+        len32 = length.to(torch.int32).contiguous()
+        B.check(B.lib().lzs_b200_pack_streams_device(
+            buf.data_ptr(), src_off.data_ptr(), len32.data_ptr(), packed.data_ptr(), dst_off.data_ptr(), n,
+            torch.cuda.current_stream(buf.device).cuda_stream))
+        return packed, dst_off
+    for s in range(n):
+        a, l, d = int(off[s]), int(length[s]), int(dst_off[s])
+        packed[d:d + l] = buf[a:a + l]
+    return packed, dst_off
+
+
+def all_gather_streams(packed, lengths, group=None, align=ALIGN):
+    """All-gather-v of packed payloads (as made by pack_streams with the same `align`).
+    Returns (payload of all ranks in rank order, lengths of all streams in rank order,
+    byte offset of every stream in the payload)."""
     world = dist.get_world_size(group)
-    lengths = lengths.to(torch.int64)
-    counts = torch.tensor([lengths.numel(), packed.numel()], dtype=torch.int64, device=packed.device)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    n_max = max(int(c[0]) for c in all_counts)
-    b_max = max(int(c[1]) for c in all_counts)
-    len_pad = torch.zeros(n_max, dtype=torch.int64, device=packed.device)
-    len_pad[:lengths.numel()] = lengths
-    pay_pad = torch.zeros(b_max, dtype=torch.uint8, device=packed.device)
-    pay_pad[:packed.numel()] = packed
-    all_len = [torch.zeros_like(len_pad) for _ in range(world)]
-    all_pay = [torch.zeros_like(pay_pad) for _ in range(world)]
-    dist.all_gather(all_len, len_pad, group=group)
-    dist.all_gather(all_pay, pay_pad, group=group)
-    lens = torch.cat([t[:int(c[0])] for t, c in zip(all_len, all_counts)])
-    payload = torch.cat([t[:int(c[1])] for t, c in zip(all_pay, all_counts)])
-    offsets = torch.cumsum(lens, 0) - lens
+    rank = dist.get_rank(group)
+    dev = packed.device
+    lengths = lengths.to(torch.int64).contiguous()
+    counts = torch.tensor([lengths.numel(), packed.numel()], dtype=torch.int64, device=dev)
+    all_counts = torch.zeros(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = all_counts.view(world, 2).cpu()
+    n_of = [int(x) for x in all_counts[:, 0]]
+    b_of = [int(x) for x in all_counts[:, 1]]
+    n_off = [sum(n_of[:r]) for r in range(world)]
+    b_off = [sum(b_of[:r]) for r in range(world)]
+    lens = torch.empty(sum(n_of), dtype=torch.int64, device=dev)
+    payload = torch.empty(sum(b_of), dtype=torch.uint8, device=dev)
+    lens[n_off[rank]:n_off[rank] + n_of[rank]] = lengths
+    payload[b_off[rank]:b_off[rank] + b_of[rank]] = packed
+    ops = []
+    for step in range(1, world):
+        to, frm = (rank + step) % world, (rank - step) % world
+        if n_of[rank]:
+            ops.append(dist.P2POp(dist.isend, lengths, to, group))
+        if n_of[frm]:
+            ops.append(dist.P2POp(dist.irecv, lens[n_off[frm]:n_off[frm] + n_of[frm]], frm, group))
+        if b_of[rank]:
+            ops.append(dist.P2POp(dist.isend, packed, to, group))
+        if b_of[frm]:
+            ops.append(dist.P2POp(dist.irecv, payload[b_off[frm]:b_off[frm] + b_of[frm]], frm, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    # offsets of the streams inside the gathered payload: every rank's part starts where the
+    # parts before it end, and inside a part streams sit at multiples of `align`
+    offsets = torch.empty_like(lens)
+    for r in range(world):
+        part = lens[n_off[r]:n_off[r] + n_of[r]]
+        off_r, _ = packed_layout(part, align)
+        offsets[n_off[r]:n_off[r] + n_of[r]] = off_r + b_off[r]
     return payload, lens, offsets

@@ -111,3 +111,36 @@ def test_chunk_layout_helper(B):
                             B._p(out_cap, B.u32p))
     assert list(in_off) == [0, 65536, 131072, 196608] and list(in_len) == [65536, 65536, 65536, 3392]
     assert list(out_off) == [0, stride, 2 * stride, 3 * stride] and set(out_cap) == {stride}
+
+
+def test_layout_is_validated_before_anything_runs(B):
+    """A stream or slot that reaches beyond the spans the caller states is refused with
+    LZS_B200_EINVAL (the device arenas are sized from the spans) -- checked before any
+    device work, so this needs no GPU."""
+    L = B.lib()
+    src = np.zeros(4096, dtype=np.uint8)
+    dst = np.zeros(8192, dtype=np.uint8)
+    out_len = np.zeros(2, dtype=np.uint32)
+    in_off = np.array([0, 1024], dtype=np.uint64)
+    in_len = np.array([1024, 1024], dtype=np.uint32)
+    out_off = np.array([0, 2048], dtype=np.uint64)
+    out_cap = np.array([2048, 2048], dtype=np.uint32)
+
+    def call(in_span, out_span, fn=L.lzs_b200_compress_batch_host):
+        return fn(B._p(src), B._p(in_off, B.u64p), B._p(in_len, B.u32p), in_span, B._p(dst), B._p(out_off, B.u64p),
+                  B._p(out_cap, B.u32p), B._p(out_len, B.u32p), out_span, 2)
+
+    assert call(2047, 4096) == -3 and b"in_span" in L.lzs_b200_last_error()
+    assert call(2048, 4095) == -3 and b"out_span" in L.lzs_b200_last_error()
+    assert call(2048, 4095, L.lzs_b200_decompress_batch_host) == -3
+    in_off[1] = 2 ** 40
+    assert call(2048, 4096) == -3
+    in_off[1] = 1024
+    used = np.zeros(1, dtype=np.uint64)
+    o2 = np.zeros(2, dtype=np.uint64)
+    assert L.lzs_b200_compress_packed_host(B._p(src), B._p(in_off, B.u64p), B._p(in_len, B.u32p), 2047, B._p(dst), 8192,
+                                           B._p(o2, B.u64p), B._p(out_len, B.u32p), 2, B._p(used, B.u64p)) == -3
+    # a well-formed call gets past the checks (and then fails or succeeds on the device question alone)
+    rc = call(2048, 4096)
+    assert rc in (0, -1), L.lzs_b200_last_error()
+    assert L.lzs_b200_release() == 0

@@ -157,9 +157,37 @@ def test_device_corpus_matches_host_corpus(B):
         assert (db.raw[:18000].cpu().numpy() == host).all()
 
 
+def _compare_all_streams(B, db, what):
+    """Every compressed stream the GPU left in db.comp against the unmodified reference (all host
+    threads, oracle/chunk_driver.c) over the same bytes: all lengths, then every byte."""
+    ref = helpers.reference() or helpers.oracle()
+    n, chunk, stride = db.n, db.chunk, db.comp_stride
+    raw = np.zeros(db.total + 16, dtype=np.uint8)
+    raw[:db.total] = db.raw[:db.total].cpu().numpy()
+    idx = np.arange(n, dtype=np.uint64)
+    in_off = idx * np.uint64(chunk)
+    in_len = db.raw_len.cpu().numpy().astype(np.uint32)
+    c_off, c_cap = idx * np.uint64(stride), np.full(n, stride, dtype=np.uint32)
+    cpu = np.zeros(n * stride + 16, dtype=np.uint8)
+    cpu_len, _ = ref.run_streams(False, raw, in_off, in_len, cpu, c_off, c_cap, os.cpu_count() or 1)
+    gpu_len = db.comp_len.cpu().numpy().astype(np.uint32)
+    bad = np.nonzero(gpu_len != cpu_len)[0]
+    assert bad.size == 0, "%s: %d of %d stream lengths differ, first at stream %d" % (what, bad.size, n, bad[0])
+    gpu = db.comp[:n * stride].cpu().numpy().reshape(n, stride)
+    cpu = cpu[:n * stride].reshape(n, stride)
+    cols = np.arange(stride, dtype=np.uint32)[None, :]
+    step = max(1, (64 << 20) // stride)
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        live = cols < gpu_len[lo:hi, None]
+        diff = (gpu[lo:hi] != cpu[lo:hi]) & live
+        assert not diff.any(), "%s: stream %d differs from the reference" % (what, lo + int(np.nonzero(diff.any(axis=1))[0][0]))
+    return n
+
+
 def test_full_size_roundtrip_1gib_64k_chunks(B):
-    """BASELINE config 2 at full size: size-independent properties (round trip, sizes within
-    LZS_COMPRESSED_MAX) plus byte-exact comparison of sampled chunks with the CPU codec."""
+    """BASELINE config 2 at full size: the round trip, sizes within LZS_COMPRESSED_MAX, and ALL
+    16 384 compressed streams byte for byte against the unmodified reference."""
     import torch
     total, chunk = 1 << 30, 65536
     db = B.DeviceBatch(total, chunk)
@@ -170,15 +198,12 @@ def test_full_size_roundtrip_1gib_64k_chunks(B):
     assert db.roundtrip_ok()
     lens = db.comp_len.cpu().numpy()
     assert lens.max() <= B.compressed_max(chunk) and lens.min() > 2
-    ref = helpers.reference() or helpers.oracle()
-    for s in (0, 1, 2, 5000, 9001, 16383):
-        raw = db.raw[s * chunk:(s + 1) * chunk].cpu().numpy().tobytes()
-        got = db.comp[s * db.comp_stride:s * db.comp_stride + int(lens[s])].cpu().numpy().tobytes()
-        assert got == ref.compress(raw), s
+    assert _compare_all_streams(B, db, "config 2") == 16384
 
 
 def test_full_size_packets_roundtrip(B):
-    """BASELINE config 3 shape: 1 Mi packets of 1500 bytes, each its own stream."""
+    """BASELINE config 3 shape: 1 Mi packets of 1500 bytes, each its own stream; the round trip and
+    ALL streams byte for byte against the unmodified reference."""
     import torch
     n, plen = 1 << 20, 1500
     db = B.DeviceBatch(n * plen, plen)
@@ -187,12 +212,47 @@ def test_full_size_packets_roundtrip(B):
     db.decompress()
     torch.cuda.synchronize()
     assert db.roundtrip_ok()
-    lens = db.comp_len.cpu().numpy()
-    ref = helpers.reference() or helpers.oracle()
-    for s in (0, 1, 2, 77777, n - 1):
-        raw = db.raw[s * plen:(s + 1) * plen].cpu().numpy().tobytes()
-        got = db.comp[s * db.comp_stride:s * db.comp_stride + int(lens[s])].cpu().numpy().tobytes()
-        assert got == ref.compress(raw), s
+    assert _compare_all_streams(B, db, "config 3") == n
+
+
+def test_exact_match_finder_launch_runs_on_hardware(B):
+    """K1's fast insert assumes sm_100a serves same-address shared-memory exchanges in ascending
+    lane order and is backed by a launch that is exact for any order (k1_match<true>), which
+    normally returns at once.  Forced here, that launch recomputes every record on the GPU: the
+    records must equal the fast launch's, and the streams the reference's."""
+    import torch
+    L = B.lib()
+    L.lzs_b200_set_force_safe_match.argtypes = [__import__("ctypes").c_int]
+    total, chunk = 24 << 20, 65536
+    db = B.DeviceBatch(total, chunk)
+    db.fill(B.CORPUS_MIXED, 0x5EED0000 + 9)
+    db.match_only()
+    torch.cuda.synchronize()
+    fast = db.scratch[256:256 + 2 * total].clone()
+    launches = L.lzs_b200_kernel_launches()
+    try:
+        L.lzs_b200_set_force_safe_match(1)
+        db.scratch[256:256 + 2 * total].zero_()
+        db.match_only()
+        torch.cuda.synchronize()
+        assert torch.equal(db.scratch[256:256 + 2 * total], fast), "the exact launch disagrees with the fast launch"
+        db.compress()
+        db.decompress()
+        torch.cuda.synchronize()
+    finally:
+        L.lzs_b200_set_force_safe_match(0)
+    assert L.lzs_b200_kernel_launches() > launches
+    assert db.roundtrip_ok()
+    _compare_all_streams(B, db, "forced exact launch")
+    packets = B.DeviceBatch(3000 * 1500, 1500)
+    packets.fill(B.CORPUS_PACKET, 0x5EED0000 + 10)
+    try:
+        L.lzs_b200_set_force_safe_match(1)
+        packets.compress()
+        torch.cuda.synchronize()
+    finally:
+        L.lzs_b200_set_force_safe_match(0)
+    _compare_all_streams(B, packets, "forced exact launch, packets")
 
 
 def test_packed_host_compression(B):
@@ -326,3 +386,59 @@ def test_torch_front_end_ragged_tensors():
         assert p[a:a + int(l)].tobytes() == d
     # a stream decoded into exactly its size stops at "output full" unless it is empty (marker seen first)
     assert all(int(s) in (0x04, 0x08) for s in status.cpu().numpy())
+
+
+@pytest.mark.parametrize("n_streams,gap", [(5, 7), (40, 3), (300, 16), (300, 0)])
+def test_host_batches_touch_nothing_outside_the_produced_bytes_slots(B, n_streams, gap):
+    """The host entry points write the out_len[s] bytes of every stream (and at most the rest of
+    its own slot) -- never a byte between slots, where a caller may keep framing.  Covers the
+    few-streams path, the sliced path with one copy per run of touching slots, and the path
+    through the pinned staging buffer (hundreds of slots with gaps)."""
+    L = B.lib()
+    o = helpers.oracle()
+    rng = np.random.default_rng(n_streams * 31 + gap)
+    data = [helpers.corpus(helpers.CORPUS_PACKET, 1, int(rng.integers(1, 1500)), first_index=i).tobytes()
+            for i in range(n_streams)]
+    want = [o.compress(d) for d in data]
+    in_off, in_len, in_span = B.layout([len(d) for d in data])
+    src = np.zeros(in_span + 64, dtype=np.uint8)
+    for off, d in zip(in_off, data):
+        src[int(off):int(off) + len(d)] = np.frombuffer(d, dtype=np.uint8)
+    caps = np.array([helpers.compressed_max(len(d)) for d in data], dtype=np.uint32)
+    out_off = np.zeros(n_streams, dtype=np.uint64)
+    pos = 5
+    for s in range(n_streams):
+        out_off[s] = pos
+        pos += int(caps[s]) + gap
+    out_span = pos
+    dst = np.full(out_span + 64, 0xA5, dtype=np.uint8)
+    out_len = np.zeros(n_streams, dtype=np.uint32)
+    B.check(L.lzs_b200_compress_batch_host(B._p(src), B._p(in_off, B.u64p), B._p(in_len, B.u32p), in_span, B._p(dst),
+                                           B._p(out_off, B.u64p), B._p(caps, B.u32p), B._p(out_len, B.u32p), out_span,
+                                           n_streams))
+    covered = np.zeros(len(dst), dtype=bool)
+    for s in range(n_streams):
+        a, l, c = int(out_off[s]), int(out_len[s]), int(caps[s])
+        assert dst[a:a + l].tobytes() == want[s], s
+        covered[a:a + c] = True
+    assert (dst[~covered] == 0xA5).all(), "bytes outside every slot were overwritten"
+    # and back, into slots with the same gaps
+    comp_off, comp_len = out_off, out_len
+    dec_cap = in_len.copy()
+    dec_off = np.zeros(n_streams, dtype=np.uint64)
+    pos = 3
+    for s in range(n_streams):
+        dec_off[s] = pos
+        pos += int(dec_cap[s]) + gap
+    back = np.full(pos + 64, 0x5A, dtype=np.uint8)
+    dec_len = np.zeros(n_streams, dtype=np.uint32)
+    B.check(L.lzs_b200_decompress_batch_host(B._p(dst), B._p(comp_off, B.u64p), B._p(comp_len, B.u32p), out_span,
+                                             B._p(back), B._p(dec_off, B.u64p), B._p(dec_cap, B.u32p),
+                                             B._p(dec_len, B.u32p), pos, n_streams))
+    covered = np.zeros(len(back), dtype=bool)
+    for s in range(n_streams):
+        a = int(dec_off[s])
+        assert back[a:a + int(dec_len[s])].tobytes() == data[s], s
+        covered[a:a + int(dec_cap[s])] = True
+    assert (back[~covered] == 0x5A).all()
+    assert L.lzs_b200_release() == 0

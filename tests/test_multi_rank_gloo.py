@@ -44,7 +44,8 @@ def _worker(rank, world, port, out_path):
         comp[s * stride:s * stride + len(c)] = np.frombuffer(c, dtype=np.uint8)
         lens[s] = len(c)
     off = torch.arange(hi - lo, dtype=torch.int64) * stride
-    packed = lzs_dist.pack_streams(torch.from_numpy(comp), off, torch.from_numpy(lens))
+    packed, packed_off = lzs_dist.pack_streams(torch.from_numpy(comp), off, torch.from_numpy(lens))
+    assert packed.numel() % 16 == 0 and all(int(x) % 16 == 0 for x in packed_off)
     payload, all_len, all_off = lzs_dist.all_gather_streams(packed, torch.from_numpy(lens))
     torch.save({"payload": payload, "len": all_len, "off": all_off, "range": (lo, hi)}, out_path % rank)
     dist.barrier()

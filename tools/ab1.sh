@@ -1,8 +1,4 @@
 mkdir -p gpurun_out
-for lanes in 8 4 16; do
-  echo "== lanes $lanes"
-  timeout 200 python tools/prof.py --mib 1024 --lanes $lanes --kind text,binary,random,mixed --iters 2 --time 2>&1 | grep -v "iter 0" | tail -6 | cut -c60-140
-  timeout 200 python tools/prof.py --mib 1024 --lanes $lanes --chunk 1500 --kind packet --iters 2 --time 2>&1 | grep -v "iter 0" | tail -2 | cut -c60-140
-  timeout 200 python tools/prof.py --mib 1024 --lanes $lanes --chunk 4096 --kind mixed --iters 2 --time 2>&1 | grep -v "iter 0" | tail -2 | cut -c60-140
-done > gpurun_out/t8_ab.log 2>&1
-cat gpurun_out/t8_ab.log
+nproc; free -g | head -2
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/t9_gpu_tests.log 2>&1; tail -5 gpurun_out/t9_gpu_tests.log
+timeout 600 python bench.py > gpurun_out/t9_bench.json 2> gpurun_out/t9_bench.err; tail -3 gpurun_out/t9_bench.err; cat gpurun_out/t9_bench.json
