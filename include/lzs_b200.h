@@ -141,6 +141,34 @@ int lzs_b200_compress_incremental_batch(LzsCompressParameters_t **params, uint32
 int lzs_b200_decompress_incremental_batch(LzsDecompressParameters_t **params, uint32_t n, size_t *produced);
 #endif
 
+/* ------------------------------------------------------------------------------
+ * The same with everything resident on the device (packet tables of flows: BASELINE configs[2]
+ * "via the incremental API"): n state blocks in device memory,
+ * lzs_b200_incremental_state_bytes() each (a multiple of 16; blocks 16-byte aligned, `stride`
+ * bytes apart), set up by lzs_b200_incremental_init_device (= lzs_compress_init /
+ * lzs_decompress_init, lzs.h:220-232), and a DEVICE array of job records, one per stream:
+ * `state`, `in`, `in_len`, `out`, `out_cap` and `add_end_marker` are the caller's inputs (the
+ * inPtr/inLength/outPtr/outLength of the reference's parameter block and the flag of
+ * lzs_compress_incremental); the call fills `in_used`, `out_used` (= the reference's return
+ * value) and `status` (LzsCompressStatus_t / LzsDecompressStatus_t bits).  One launch, one warp
+ * per stream, nothing crosses PCIe; the caller advances its pointers by in_used / out_used and
+ * calls again until LZS_C_STATUS_END_MARKER, exactly as c/src/utils/lzs-compress.c:91-134 does.
+ * The history survives end markers, so a flow's packets share it (RFC 1974 style).
+ * ---------------------------------------------------------------------------- */
+typedef struct {
+    void          *state;
+    const uint8_t *in;
+    uint8_t       *out;
+    uint32_t       in_len, out_cap;
+    uint32_t       in_used, out_used, status;
+    uint32_t       add_end_marker;
+} lzs_b200_inc_job_t;
+
+size_t lzs_b200_incremental_state_bytes(int decompress);
+int    lzs_b200_incremental_init_device(void *states, size_t stride, uint32_t n_streams, int decompress, void *stream);
+int    lzs_b200_compress_incremental_batch_device(lzs_b200_inc_job_t *jobs, uint32_t n_streams, void *stream);
+int    lzs_b200_decompress_incremental_batch_device(lzs_b200_inc_job_t *jobs, uint32_t n_streams, void *stream);
+
 /* Uniform chunking helpers (host arrays): stream s covers [s*chunk, min((s+1)*chunk, total))
  * and its output slot starts at s*out_stride. */
 uint32_t lzs_b200_chunk_count(uint64_t total, uint32_t chunk);

@@ -85,8 +85,25 @@ __device__ __forceinline__ uint32_t ring_add(uint32_t idx, uint32_t inc, uint32_
 
 /* ------------------------------------------------------------------ compress */
 
-/* One call of lzs_compress_incremental; whole warp, uniform control flow. */
-__device__ inline void inc_compress_call(IncCompressState *S, IncJob *J)
+/* Copy `bytes` bytes between a 4-byte aligned global address and shared memory (whole warp). */
+__device__ __forceinline__ void inc_copy_ring(uint8_t *dst, const uint8_t *src, uint32_t bytes)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t words = bytes >> 2;
+    if ((reinterpret_cast<uintptr_t>(src) & 3u) == 0u && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0u) {
+        for (uint32_t w = lane; w < words; w += 32u)
+            reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<const uint32_t *>(src)[w];
+        for (uint32_t b = 4u * words + lane; b < bytes; b += 32u) dst[b] = src[b];
+    } else {
+        for (uint32_t b = lane; b < bytes; b += 32u) dst[b] = src[b];
+    }
+    __syncwarp();
+}
+
+/* One call of lzs_compress_incremental; whole warp, uniform control flow.  `ring` is the warp's
+ * shared-memory copy of the state's ring for the duration of the call (the search reads it
+ * thousands of times per token): loaded on entry, written back on exit. */
+__device__ inline void inc_compress_call(IncCompressState *S, IncJob *J, uint8_t *ring)
 {
     const uint32_t lane = lane_id();
     const bool     finish = J->add_end_marker != 0;
@@ -96,7 +113,14 @@ __device__ inline void inc_compress_call(IncCompressState *S, IncJob *J)
     uint32_t       status = 0;
     uint32_t       queue = S->queue, qlen = S->qlen, latest = S->latest, la_idx = S->la_idx;
     uint32_t       hist_len = S->hist_len, moff = S->offset, la_len = S->la_len, ext = S->extended;
-    uint8_t       *ring = S->ring;
+    /* nothing offered, nothing asked for, nothing to flush: the reference's loop (:574-610) stops
+     * at once with "finished | starved" -- no need to bring the ring in for that */
+    if (in_left == 0 && !finish && qlen < 8u) {
+        __syncwarp();
+        if (lane == 0) { J->in_used = 0; J->out_used = 0; J->status = kStFinished | kStStarved; }
+        return;
+    }
+    inc_copy_ring(ring, S->ring, kIncCRing);
 
     for (;;) {
         uint32_t length = 0;
@@ -124,9 +148,13 @@ __device__ inline void inc_compress_call(IncCompressState *S, IncJob *J)
                 const uint32_t M = umin32(la_len, kSearchMax);
                 uint32_t       key = 0;
                 if (M >= kMinLen) {
+                    /* the window already in the ring, offsets lane+1, lane+33, ...: an offset whose
+                     * first byte differs (nearly all of them) costs one load and one compare */
+                    const uint32_t first = ring[latest];
                     for (uint32_t o = lane + 1u; o <= hist_len; o += 32u) {
                         const uint32_t from = ring_add(latest, kIncCRing - o, kIncCRing);
-                        uint32_t       l = 0;
+                        if (ring[from] != first) continue;
+                        uint32_t l = 1;
                         while (l < M && ring[ring_add(latest, l, kIncCRing)] == ring[ring_add(from, l, kIncCRing)]) l++;
                         const uint32_t cand = (l << 12) | (4095u - o);
                         if (l >= kMinLen && cand > key) key = cand;
@@ -179,6 +207,7 @@ __device__ inline void inc_compress_call(IncCompressState *S, IncJob *J)
     }
 
     __syncwarp();
+    if (in_pos != 0) inc_copy_ring(S->ring, ring, kIncCRing);   /* the ring only changes where input is appended */
     if (lane == 0) {
         S->queue = queue; S->qlen = static_cast<uint8_t>(qlen); S->latest = static_cast<uint16_t>(latest);
         S->la_idx = static_cast<uint16_t>(la_idx); S->hist_len = static_cast<uint16_t>(hist_len);
@@ -322,8 +351,19 @@ __device__ inline void inc_decompress_call(IncDecompressState *S, IncJob *J)
 __global__ void __launch_bounds__(128)
 kinc_compress(IncJob *jobs, uint32_t n)
 {
+    __shared__ __align__(16) uint8_t s_ring[4][(kIncCRing + 15) / 16 * 16];
     const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j < n) inc_compress_call(static_cast<IncCompressState *>(jobs[j].state), &jobs[j]);
+    if (j < n) inc_compress_call(static_cast<IncCompressState *>(jobs[j].state), &jobs[j], s_ring[threadIdx.x >> 5]);
+}
+
+/* Fresh states for n streams, `stride` bytes apart (device memory). */
+__global__ void kinc_init(uint8_t *states, size_t stride, uint32_t n, int decompress)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t *w = reinterpret_cast<uint32_t *>(states + static_cast<size_t>(j) * stride);
+    w[0] = w[1] = w[2] = w[3] = 0;                       /* both headers are 16 bytes; the rings need no clearing */
+    if (decompress) reinterpret_cast<IncDecompressState *>(w)->state = kDTokenType;
 }
 
 __global__ void __launch_bounds__(128)

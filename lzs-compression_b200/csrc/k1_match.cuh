@@ -547,6 +547,78 @@ __device__ __forceinline__ void k1_store_grams(const K1Words &r, uint32_t *W, co
     }
 }
 
+#ifndef LZS_K1_BULK
+#define LZS_K1_BULK 0                       /* 1: the loader stages the input with cp.async.bulk (TMA, 1-D) instead of word loads */
+#endif
+#if defined(LZS_SIMT_EMU)
+#undef LZS_K1_BULK
+#define LZS_K1_BULK 0                       /* the emulator has no asynchronous copy engine */
+#endif
+constexpr uint32_t kK1StageBytes = 576;     /* a tile's new bytes (448 + 40 + 3) plus alignment on both sides, rounded up */
+
+#if LZS_K1_BULK
+/* One tile's input bytes, requested from the copy engine: [a0, a0 + bytes) is the 16-byte aligned
+ * range that covers the bytes q_lo .. hi_b-1 of the stream (bytes == 0: nothing to fetch). */
+struct K1Stage {
+    uintptr_t a0;
+    uint32_t  bytes;
+};
+__device__ __forceinline__ K1Stage k1_stage_range(const uint8_t *src, uint32_t q_lo, uint32_t q_hi, uint32_t n)
+{
+    K1Stage        s;
+    const uint32_t hi_b = umin32(q_hi + 3u, n);                     /* grams reach 3 bytes on; nothing past the stream */
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(src) + q_lo, hi = reinterpret_cast<uintptr_t>(src) + hi_b;
+    s.a0 = lo & ~static_cast<uintptr_t>(15);
+    s.bytes = hi_b > q_lo ? static_cast<uint32_t>(((hi + 15u) & ~static_cast<uintptr_t>(15)) - s.a0) : 0u;
+    return s;
+}
+/* lane 0: arm the barrier with the byte count and start the copy (global -> shared, completes on the barrier) */
+__device__ __forceinline__ void k1_stage_issue(uint8_t *stage, uint64_t *bar, const K1Stage &r)
+{
+    const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(stage));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    /* earlier reads of the buffer, then the engine's writes */
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(b), "r"(r.bytes) : "memory");
+    if (r.bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(r.a0), "r"(r.bytes), "r"(b) : "memory");
+}
+/* grams p_lo .. p_hi-1 of the stream from the staged bytes: lane l makes the four grams 4l .. 4l+3
+ * of every 128-position group out of three staged words */
+__device__ __forceinline__ void k1_store_grams_staged(const uint8_t *stage, const K1Stage &r, uint32_t *W,
+                                                      const uint8_t *src, uint32_t v0, uint32_t p_lo, uint32_t p_hi,
+                                                      uint32_t n)
+{
+    const uint32_t  lane = lane_id();
+    const uint32_t  lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) + p_lo - r.a0);   /* 0..15 */
+    const uint32_t  m = lead & 3u;                                                                 /* warp-uniform */
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (lead >> 2);
+    const uint32_t  words = r.bytes >> 2;
+#pragma unroll
+    for (int k = 0; k < kK1LoadGroups; k++) {
+        const uint32_t wi = static_cast<uint32_t>(k) * 32u + lane;
+        const uint32_t q0 = p_lo + static_cast<uint32_t>(k) * 128u + 4u * lane;
+        if (q0 >= p_hi) continue;
+        const uint32_t base = (lead >> 2) + wi;
+        const uint32_t x0 = base < words ? sw[wi] : 0u;
+        const uint32_t x1 = base + 1u < words ? sw[wi + 1u] : 0u;
+        const uint32_t x2 = base + 2u < words ? sw[wi + 2u] : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t o = m + j;                     /* byte offset from word wi: 0..6 */
+            const uint32_t g = __funnelshift_r(o < 4u ? x0 : x1, o < 4u ? x1 : x2, (o & 3u) * 8u);
+            const uint32_t q = q0 + j;
+            if (q < p_hi) {
+                const uint32_t x = (v0 + q) & (kK1WRing - 1);
+                const uint32_t w = (q < n) ? g : 0u;
+                W[x] = w;
+                if (x < kK1WMirror) W[kK1WRing + x] = w;
+            }
+        }
+    }
+}
+#endif
+
 /* Queries of one tile, handed out in chunks of 32 positions (one per warp pass) from a counter in
  * shared memory, so that a warp that drew cheap positions takes more of them. */
 __device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_chunk, const uint16_t *links,
@@ -589,6 +661,10 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     __shared__ uint32_t s_filled;            /* tiles whose grams and descriptor are in place     */
     __shared__ uint32_t s_qdone[kK1Depth];   /* query-warp completions per stage: tile q is done at 16 (q / depth + 1) in [q % depth] */
     __shared__ uint32_t s_qnext[16];         /* next chunk of tile g to query, in s_qnext[g & 15]  */
+#if LZS_K1_BULK
+    __shared__ __align__(128) uint8_t s_stage[2][kK1StageBytes];   /* input bytes of the tile being filled and the next */
+    __shared__ uint64_t              s_stage_bar[2];
+#endif
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
@@ -603,6 +679,10 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
         mbar_init(&s_full[tid], kK1BuildThreads);
         mbar_init(&s_empty[tid], kK1QueryThreads);
     }
+#if LZS_K1_BULK
+    if (tid < 2) mbar_init(&s_stage_bar[tid], 1);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     __syncthreads();
 
     if (warp == static_cast<uint32_t>(kK1BuildWarps)) {
@@ -612,6 +692,9 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          * critical path and the build warps never have to meet each other. */
         uint32_t g = 0;                      /* tiles described so far                  */
         uint32_t vnext = 4096;               /* virtual position of the next stream     */
+#if LZS_K1_BULK
+        uint32_t stage_n = 0;                /* staging requests consumed so far: buffer and barrier phase */
+#endif
         for (;;) {
             uint32_t sid = 0;
             if (lane == 0) sid = atomicAdd(next_stream, 1u);
@@ -628,13 +711,31 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
              * 32 positions whose hashes the build warps prefetch in their last batch.  The words of
              * the NEXT tile are requested before this tile's grams are written, so the DRAM latency
              * is paid once per stream, not once per tile. */
+#if LZS_K1_BULK
+            /* the copy engine brings the tile's bytes into one of two staging buffers (a tile ahead,
+             * like the word loads of the other variant); the loader turns them into grams */
+            (void)wlast;
+            K1Stage cur = k1_stage_range(src, 0u, umin32(kK1Tile + kK1Ahead, n + 12u), n);
+            if (lane == 0) k1_stage_issue(s_stage[stage_n & 1u], &s_stage_bar[stage_n & 1u], cur);
+#else
             K1Words cur;
             k1_load_words(cur, src, 0u, wlast);
+#endif
             for (uint32_t t0 = 0; t0 < n; t0 += kK1Tile, g++) {
                 const uint32_t p_lo = (t0 == 0) ? 0u : t0 + kK1Ahead;
                 const uint32_t p_hi = umin32(t0 + kK1Tile + kK1Ahead, n + 12u);
+#if LZS_K1_BULK
+                const uint32_t t1 = t0 + kK1Tile;
+                K1Stage        nxt = {0, 0};
+                if (t1 < n) {
+                    nxt = k1_stage_range(src, t1 + kK1Ahead, umin32(t1 + kK1Tile + kK1Ahead, n + 12u), n);
+                    __syncwarp();
+                    if (lane == 0) k1_stage_issue(s_stage[(stage_n + 1u) & 1u], &s_stage_bar[(stage_n + 1u) & 1u], nxt);
+                }
+#else
                 K1Words nxt;
                 k1_load_words(nxt, src, t0 + kK1Tile + kK1Ahead, wlast);
+#endif
                 if (g > kK1Depth) {          /* every query warp has left tile g - depth - 1 */
                     const uint32_t q = g - kK1Depth - 1u;
                     while (*reinterpret_cast<volatile uint32_t *>(&s_qdone[q & (kK1Depth - 1u)]) <
@@ -642,8 +743,15 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         spin_pause();
                     __threadfence_block();
                 }
+#if LZS_K1_BULK
+                mbar_wait(&s_stage_bar[stage_n & 1u], (stage_n >> 1) & 1u);
+                k1_store_grams_staged(s_stage[stage_n & 1u], cur, W, src, v0, p_lo, p_hi, n);
+                stage_n++;
+                cur = nxt;
+#else
                 k1_store_grams(cur, W, src, v0, p_lo, p_hi, n);
                 cur = nxt;
+#endif
                 if (lane == 0) {
                     K1Tile d;
                     d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0;

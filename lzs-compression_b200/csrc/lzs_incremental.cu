@@ -276,6 +276,47 @@ size_t lzs_decompress_incremental(LzsDecompressParameters_t *pParams)
     return one_call(true, pParams, false);
 }
 
+/* ---- device-resident batches: states, job table, input and output all in device memory ---- */
+
+static_assert(sizeof(lzs_b200_inc_job_t) == sizeof(lzs::IncJob) && offsetof(lzs_b200_inc_job_t, status) == offsetof(lzs::IncJob, status) &&
+                  offsetof(lzs_b200_inc_job_t, add_end_marker) == offsetof(lzs::IncJob, add_end_marker),
+              "the public job record is the kernels' job record");
+static_assert(offsetof(lzs::IncCompressState, ring) == 16 && offsetof(lzs::IncDecompressState, ring) == 16, "16-byte headers");
+
+size_t lzs_b200_incremental_state_bytes(int decompress)
+{
+    return ((decompress ? kIncDBytes : kIncCBytes) + 15) / 16 * 16;
+}
+
+int lzs_b200_incremental_init_device(void *states, size_t stride, uint32_t n_streams, int decompress, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!states || stride < lzs_b200_incremental_state_bytes(decompress) || (stride & 15u) ||
+        (reinterpret_cast<uintptr_t>(states) & 15u))
+        return LZS_B200_EINVAL;
+    lzs::kinc_init<<<(n_streams + 255u) / 256u, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint8_t *>(states), stride, n_streams, decompress);
+    return cudaGetLastError() == cudaSuccess ? LZS_B200_OK : LZS_B200_ECUDA;
+}
+
+int lzs_b200_compress_incremental_batch_device(lzs_b200_inc_job_t *jobs, uint32_t n_streams, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!jobs) return LZS_B200_EINVAL;
+    const unsigned grid = (n_streams + 3u) / 4u;
+    lzs::kinc_compress<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<lzs::IncJob *>(jobs), n_streams);
+    return cudaGetLastError() == cudaSuccess ? LZS_B200_OK : LZS_B200_ECUDA;
+}
+
+int lzs_b200_decompress_incremental_batch_device(lzs_b200_inc_job_t *jobs, uint32_t n_streams, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!jobs) return LZS_B200_EINVAL;
+    const unsigned grid = (n_streams + 3u) / 4u;
+    lzs::kinc_decompress<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<lzs::IncJob *>(jobs), n_streams);
+    return cudaGetLastError() == cudaSuccess ? LZS_B200_OK : LZS_B200_ECUDA;
+}
+
 /* Batch forms: advance n independent streams by one incremental call each, one warp
  * per stream in a single launch.  produced[s] (optional) receives each call's return
  * value. */

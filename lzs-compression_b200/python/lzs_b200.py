@@ -299,3 +299,69 @@ class DeviceBatch:
 
     def compressed_bytes(self):
         return int(self.comp_len.to(self.torch.int64).sum().item())
+
+
+# ------------------------------------------------ device-resident incremental batches
+
+class DeviceFlows:
+    """n flows advanced together through the incremental API with everything resident on the
+    device (include/lzs_b200.h: lzs_b200_*_incremental_batch_device).  Plumbing only: torch holds
+    the state blocks and the job table; every call is ONE launch, nothing crosses PCIe.
+    Job record (48 bytes) as six int64 columns: state, in, out, in_len | out_cap << 32,
+    in_used | out_used << 32, status | add_end_marker << 32."""
+
+    def __init__(self, n, decompress=False, device="cuda:0"):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.n = int(n)
+        self.decompress = bool(decompress)
+        L = lib()
+        L.lzs_b200_incremental_state_bytes.restype = ctypes.c_size_t
+        L.lzs_b200_incremental_state_bytes.argtypes = [ctypes.c_int]
+        vp = ctypes.c_void_p
+        L.lzs_b200_incremental_init_device.argtypes = [vp, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, vp]
+        L.lzs_b200_compress_incremental_batch_device.argtypes = [vp, ctypes.c_uint32, vp]
+        L.lzs_b200_decompress_incremental_batch_device.argtypes = [vp, ctypes.c_uint32, vp]
+        self.stride = int(L.lzs_b200_incremental_state_bytes(int(self.decompress)))
+        self.states = torch.empty(self.n * self.stride, dtype=torch.uint8, device=self.device)
+        self.jobs = torch.zeros((self.n, 6), dtype=torch.int64, device=self.device)
+        self.jobs[:, 0] = self.states.data_ptr() + torch.arange(self.n, dtype=torch.int64, device=self.device) * self.stride
+        self.init()
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def init(self):
+        check(lib().lzs_b200_incremental_init_device(self.states.data_ptr(), self.stride, self.n, int(self.decompress),
+                                                      self._stream()))
+
+    def offer(self, in_ptr, in_len, out_ptr, out_cap, add_end_marker=True):
+        """Set inPtr/inLength/outPtr/outLength of every flow (int64 tensors of device addresses / sizes)."""
+        j = self.jobs
+        j[:, 1] = in_ptr
+        j[:, 2] = out_ptr
+        j[:, 3] = in_len.to(self.torch.int64) | (out_cap.to(self.torch.int64) << 32)
+        j[:, 4] = 0
+        j[:, 5] = (1 if add_end_marker else 0) << 32
+
+    def call(self):
+        """One lzs_*_incremental call for every flow; then advance pointers and lengths as the
+        reference does in its parameter block.  Returns (in_used, out_used, status) tensors."""
+        f = lib().lzs_b200_decompress_incremental_batch_device if self.decompress else \
+            lib().lzs_b200_compress_incremental_batch_device
+        check(f(self.jobs.data_ptr(), self.n, self._stream()))
+        j = self.jobs
+        m32 = 0xFFFFFFFF
+        in_used, out_used = j[:, 4] & m32, (j[:, 4] >> 32) & m32
+        status = j[:, 5] & m32
+        in_len, out_cap = (j[:, 3] & m32) - in_used, ((j[:, 3] >> 32) & m32) - out_used
+        j[:, 1] += in_used
+        j[:, 2] += out_used
+        j[:, 3] = in_len | (out_cap << 32)
+        # a flow that has written its end marker is not called for again (the caller's loop of
+        # c/src/utils/lzs-compress.c:91 ends there): no input, no marker request
+        done = (status & 0x04) != 0
+        flag = self.torch.where(done, self.torch.zeros_like(status), (j[:, 5] >> 32) & 1)
+        j[:, 5] = flag << 32
+        return in_used.clone(), out_used.clone(), status.clone()

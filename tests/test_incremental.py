@@ -243,3 +243,24 @@ def test_gpu_flows_with_shared_history_across_packets():
             assert stat & D.END_MARKER and used == len(c)
             back += dst[:ret].tobytes()
         assert back == b"".join(pk)
+
+
+@pytest.mark.gpu
+def test_gpu_device_resident_flows_through_the_incremental_api():
+    """lzs_b200_*_incremental_batch_device: states, job table, input and output all on the device.
+    tools/inc_device_bench.py runs init + incremental until END_MARKER for every flow, compares every
+    flow with the batch compressor, the call traces of a sample with the unmodified reference, a
+    second packet on the kept history with the reference, and decodes both packets of every flow
+    through one device-resident decoder state."""
+    import json
+    import subprocess
+    import sys
+    tool = os.path.join(helpers.ROOT, "tools", "inc_device_bench.py")
+    r = subprocess.run([sys.executable, tool, "--flows", "6000", "--sample", "96"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["flows_equal_to_batch_compressor"] == 6000
+    if os.path.exists(helpers.REF_SO):
+        assert line["call_traces_equal_to_reference"] == 96 and line["second_packet_on_kept_history_checked"] == 64
+    assert line["ratio_second_packet_kept_history"] > line["ratio_first_packet"]
