@@ -73,6 +73,9 @@ constexpr uint32_t kK1WMirror = 64;         /* the first grams again behind the 
 #ifndef LZS_K1_TILE
 #define LZS_K1_TILE 448
 #endif
+#ifndef LZS_K1_EAGER
+#define LZS_K1_EAGER 0                      /* 1: a query step loads the candidate's bytes together with its link entry */
+#endif
 #ifndef LZS_K1_BUILD_UNROLL
 #define LZS_K1_BUILD_UNROLL 2
 #endif
@@ -97,7 +100,7 @@ constexpr bool     kK1Grouped = LZS_K1_GROUPED != 0;
 /* one warp per level + the run-table warp, or a group of levels per warp (the last one also builds the run table) */
 constexpr int      kK1BuildWarps = kK1Lpw == 1 ? kK1Levels + 1 : (kK1Levels + kK1Lpw - 1) / kK1Lpw;
 #ifndef LZS_K1_QW
-#define LZS_K1_QW 16
+#define LZS_K1_QW 18
 #endif
 constexpr int      kK1QueryWarps = LZS_K1_QW;
 constexpr int      kK1Threads = 32 * (kK1BuildWarps + 1 + kK1QueryWarps);   /* + the loader warp */
@@ -461,6 +464,15 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
         walked++;
         const uint32_t j = v - tot;
         e = lk[j & (kK1LinkRing - 1)];
+#if LZS_K1_EAGER
+        /* the candidate's twelve bytes are requested together with its link entry: one
+         * shared-memory round trip per step instead of two when the entry is one of ours */
+        const uint32_t *wje = W + (j & (kK1WRing - 1));
+        const uint32_t  y0 = wje[0], y1 = wje[4], y2 = wje[8];
+#ifndef LZS_SIMT_EMU
+        asm volatile("" ::"r"(e), "r"(y0), "r"(y1), "r"(y2));
+#endif
+#endif
         d = e & kLinkDistMask;
         if ((e >> 11) != tag) {                              /* foreign entry of this slot  */
             LZS_STAT(2, 1);
@@ -479,8 +491,12 @@ __device__ __forceinline__ uint32_t k1_query(const uint16_t *links, const uint16
             }
             continue;
         }
+#if LZS_K1_EAGER
+        const uint32_t l = umin32(lcp12(w0, w1, w2, y0, y1, y2), M);
+#else
         const uint32_t *wj = W + (j & (kK1WRing - 1));
         const uint32_t l = umin32(lcp12(w0, w1, w2, wj[0], wj[4], wj[8]), M);
+#endif
         if (l < k) { LZS_STAT(3, 1); continue; }
         LZS_STAT(4, 1);
         best = l;                                            /* nearest candidate of length l */
@@ -547,6 +563,9 @@ __device__ __forceinline__ void k1_store_grams(const K1Words &r, uint32_t *W, co
     }
 }
 
+#ifndef LZS_K1_EAGER
+#define LZS_K1_EAGER 0                      /* 1: a query step loads the candidate's bytes together with its link entry */
+#endif
 #ifndef LZS_K1_BULK
 #define LZS_K1_BULK 0                       /* 1: the loader stages the input with cp.async.bulk (TMA, 1-D) instead of word loads */
 #endif

@@ -14,6 +14,7 @@ static int TAGBITS = 5;
 
 static int HASHMODE = 0;
 static int GALLOP = 2;
+static int LEVELS = 0x1FFC;   /* bit k set: level k has a table */
 static inline uint32_t rolling_hash(const uint8_t *p, int k)
 {
     // groups of levels as the build warps compute them: {2,3,4} {5,6,7} {8,9,10} {11,12}
@@ -75,9 +76,10 @@ int main(int argc, char **argv)
     TAGBITS = argc > 4 ? atoi(argv[4]) : 5;
     HASHMODE = argc > 5 ? atoi(argv[5]) : 0;
     GALLOP = argc > 6 ? atoi(argv[6]) : 2;
+    LEVELS = argc > 7 ? (int)strtol(argv[7], 0, 0) : 0x1FFC;
     const int n = 65536;
     std::vector<uint8_t> buf(n + 64, 0);
-    Stats cur, v1, v2, v3, v4;
+    Stats cur, v1, v2, v3, v4, v5;
     double lenhist[13] = {0};
     for (int s = 0; s < nstreams; s++) {
         memset(buf.data(), 0, buf.size());
@@ -109,7 +111,7 @@ int main(int argc, char **argv)
                 }
             }
         // queries
-        std::vector<int> c0(n), c1(n), c2(n), c3(n), c4(n), needB(n), lenbest(n);
+        std::vector<int> c0(n), c1(n), c2(n), c3(n), c4(n), c5(n), needB(n), lenbest(n);
         for (int i = 1; i + 12 <= n; i++) {
             const int M = 12, maxd = std::min(W, i);
             // ---- V0: current upward walk; steps = chain hops (LDS of entries)
@@ -209,6 +211,31 @@ int main(int argc, char **argv)
                 c4[i] = steps;
                 if (best != (int)lenbest[i]) { fprintf(stderr, "V4 mismatch at %d: %d vs %d\n", i, best, lenbest[i]); exit(1); }
             }
+            // ---- V5: sparse levels: level k is looked up on the chain of the largest BUILT level <= k
+            {
+                int k = 2, steps = 0, best = 0;
+                for (;;) {
+                    int kb = k;
+                    while (!(LEVELS >> kb & 1)) kb--;
+                    int tot = 0, d = L[kb].d1[i];
+                    bool found = false;
+                    steps++;
+                    while (d && tot + d <= maxd) {
+                        tot += d;
+                        int j = i - tot;
+                        steps++;
+                        d = L[kb].d1[j];
+                        if (L[kb].tag[j] != L[kb].tag[i]) continue;
+                        int l = lcp(&buf[i], &buf[j], M);
+                        if (l < k) continue;
+                        best = l; found = true; break;
+                    }
+                    if (!found || best >= M) break;
+                    k = best + 1;
+                }
+                c5[i] = steps;
+                if (best != (int)lenbest[i]) { fprintf(stderr, "V5 mismatch at %d: %d vs %d\n", i, best, lenbest[i]); exit(1); }
+            }
             // ---- V3: plain upward walk (V0) but with collapse skip
             {
                 int k = 2, steps = 0, best = 0;
@@ -239,7 +266,7 @@ int main(int argc, char **argv)
                 st.maxsum += mx; st.passes++;
             }
         };
-        acc(cur, c0); acc(v1, c1); acc(v2, c2); acc(v3, c3); acc(v4, c4);
+        acc(cur, c0); acc(v1, c1); acc(v2, c2); acc(v3, c3); acc(v4, c4); acc(v5, c5);
         // phase B for V2: compact unresolved positions of a 448 tile into groups of 32
         for (int t = 32; t + 448 <= n - 12; t += 448) {
             std::vector<int> list;
@@ -261,6 +288,7 @@ int main(int argc, char **argv)
     pr("V0 current upward", cur);
     pr("V3 upward+collapse", v3);
     pr("V4 gallop+binary", v4);
+    { char nm[64]; snprintf(nm, sizeof nm, "V5 sparse levels %03x", LEVELS >> 2); pr(nm, v5); }
     pr("V1 mask start", v1);
     pr("V2 mask start+collapse", v2);
     printf("  V2 two-phase: walkers %.1f%%  B steps/walker %.2f  B warp-max %.2f  B passes per 448-tile %.2f -> B max-steps per pos %.3f\n",
