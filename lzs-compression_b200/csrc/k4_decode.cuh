@@ -84,7 +84,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
           const uint32_t *__restrict__ in_len, uint8_t *__restrict__ out,
           const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
           uint32_t *__restrict__ out_len, uint32_t n_streams, uint32_t *__restrict__ next_stream,
-          uint8_t *__restrict__ status)
+          uint8_t *__restrict__ status, const uint32_t *__restrict__ order)
 {
     LZS_DYN_SMEM(uint8_t, smem);
     const uint32_t lane = lane_id();
@@ -140,7 +140,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 if (s >= n_streams) {
                     exhausted = true;
                 } else {
-                    sid = s;
+                    sid = order ? order[s] : s;             /* streams in the order the launcher chose */
                     const uint8_t  *p = in + in_off[sid];
                     const uint32_t  nin = umin32(in_len[sid], 0x1FFFFF00u);   /* 32-bit bit positions */
                     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -318,6 +318,55 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             active = false;
         }
     }
+}
+
+/* ---- launch order of the streams ----
+ * The groups of a warp decode in lock step, so a warp costs what its slowest stream costs, and
+ * the launch ends when the last stream does.  Streams of similar density (compressed bytes per
+ * byte of capacity: mostly literals / mixed / mostly long matches) take similar numbers of
+ * rounds, so the launcher hands them out bucket by bucket -- warps get streams of one kind --
+ * in the order of rising density: the streams made of literals, which decode fastest, come last
+ * and fill the tail of the launch.  A counting sort into 16 buckets: counters, then slots. */
+constexpr uint32_t kDecBuckets = 16;
+__device__ __forceinline__ uint32_t k4_bucket(uint32_t in_len, uint32_t cap)
+{
+    if (cap == 0u) return kDecBuckets - 1u;
+    const uint64_t b = (static_cast<uint64_t>(in_len) * 12u) / cap;        /* 12 per unit of density: literals-only is 1.125 */
+    return b < kDecBuckets - 1u ? static_cast<uint32_t>(b) : kDecBuckets - 1u;
+}
+__global__ void k4_order_count(const uint32_t *__restrict__ in_len, const uint32_t *__restrict__ out_cap, uint32_t n,
+                               uint32_t *__restrict__ counts)
+{
+    __shared__ uint32_t s_c[kDecBuckets];
+    if (threadIdx.x < kDecBuckets) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) atomicAdd(&s_c[k4_bucket(in_len[s], out_cap[s])], 1u);
+    __syncthreads();
+    if (threadIdx.x < kDecBuckets && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_c[threadIdx.x]);
+}
+/* counts[0..16) = bucket sizes in, running cursors out (counts[16..32) is used for them) */
+__global__ void k4_order_scatter(const uint32_t *__restrict__ in_len, const uint32_t *__restrict__ out_cap, uint32_t n,
+                                 uint32_t *__restrict__ counts, uint32_t *__restrict__ order)
+{
+    __shared__ uint32_t s_base[kDecBuckets], s_c[kDecBuckets], s_at[kDecBuckets];
+    if (threadIdx.x < kDecBuckets) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t       b = 0, rank = 0;
+    if (s < n) {
+        b = k4_bucket(in_len[s], out_cap[s]);
+        rank = atomicAdd(&s_c[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kDecBuckets) {
+        uint32_t start = 0;
+        for (uint32_t k = 0; k < threadIdx.x; k++) start += counts[k];
+        s_base[threadIdx.x] = start;
+        s_at[threadIdx.x] = s_c[threadIdx.x] ? atomicAdd(&counts[kDecBuckets + threadIdx.x], s_c[threadIdx.x]) : 0u;
+    }
+    __syncthreads();
+    if (s < n) order[s_base[b] + s_at[b] + rank] = s;
 }
 
 }  // namespace lzs

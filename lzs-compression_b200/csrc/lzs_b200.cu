@@ -103,6 +103,17 @@ int decode_lanes()
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+/* LZS_B200_ORDER=0 turns the decoder's launch order off (streams in index order), for measurements */
+bool order_streams()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_ORDER");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 constexpr size_t kCounterBytes = 256;    /* work counters live at the start of scratch */
 
 __global__ void corpus_fill_kernel(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
@@ -163,6 +174,12 @@ size_t lzs_b200_compress_scratch_bytes(uint64_t in_span)
 }
 
 size_t lzs_b200_decompress_scratch_bytes(void) { return kCounterBytes; }
+
+/* with room for the launch order of n streams (see k4_decode.cuh) */
+size_t lzs_b200_decompress_scratch_bytes_for(uint32_t n_streams)
+{
+    return kCounterBytes + align_up(static_cast<size_t>(n_streams) * sizeof(uint32_t), 256);
+}
 
 int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                                 uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream)
@@ -246,7 +263,19 @@ int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *i
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t    *counter = static_cast<uint32_t *>(scratch);
-    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, kCounterBytes, st));
+    /* launch order: streams of similar density together, the fastest kind last (k4_decode.cuh);
+     * needs scratch for one index per stream, otherwise the streams go in index order */
+    const uint32_t *order = nullptr;
+    if (n_streams >= 1024u && scratch_bytes >= lzs_b200_decompress_scratch_bytes_for(n_streams) && order_streams()) {
+        uint32_t *ord = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(scratch) + kCounterBytes);
+        uint32_t *counts = counter + 8;                  /* 32 words inside the counter block */
+        const unsigned blocks = (n_streams + 255u) / 256u;
+        lzs::k4_order_count<<<blocks, 256, 0, st>>>(in_len, out_cap, n_streams, counts);
+        lzs::k4_order_scatter<<<blocks, 256, 0, st>>>(in_len, out_cap, n_streams, counts, ord);
+        g_launches += 2;
+        order = ord;
+    }
     const int lanes = decode_lanes();
     const int idx = lanes == 4 ? 0 : lanes == 8 ? 1 : lanes == 16 ? 2 : 3;
     const unsigned per_block = lzs::kDecThreads / lanes;
@@ -256,19 +285,19 @@ int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *i
     switch (lanes) {
         case 4:
             lzs::k4_decode<4><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<4>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
             break;
         case 16:
             lzs::k4_decode<16><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<16>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
             break;
         case 32:
             lzs::k4_decode<32><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<32>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
             break;
         default:
             lzs::k4_decode<8><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<8>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
             break;
     }
     g_launches++;
@@ -644,7 +673,7 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     HostPath     &p = *hp;
     PipelineScope scope(p);                 /* declared after the lock: drains before the arena is released */
     cudaStream_t  st = p.stream;
-    const size_t  scratch = decompress ? lzs_b200_decompress_scratch_bytes() : lzs_b200_compress_scratch_bytes(in_span);
+    const size_t  scratch = decompress ? lzs_b200_decompress_scratch_bytes_for(n) : lzs_b200_compress_scratch_bytes(in_span);
     if ((rc = p.reserve(S_IN, in_span + 64))) return rc;
     if ((rc = p.reserve(S_OUT, out_span + 64))) return rc;
     if ((rc = p.reserve(S_INOFF, n * sizeof(uint64_t)))) return rc;

@@ -16,7 +16,7 @@ static void run_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t
 {
     uint32_t counter = 0;
     simt::launch(dim3(grid), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<G>(), [&] {
-        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter, status);
+        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter, status, nullptr);
     });
 }
 

@@ -1,7 +1,10 @@
 mkdir -p gpurun_out
-for v in default eager eq20 q18 q20 t384 t320 u1; do
-  if [ $v = default ]; then lib=lzs-compression_b200/liblzs.so; else lib=variants/$v.so; fi
-  echo "== $v"
-  LZS_B200_LIB=$PWD/$lib timeout 200 python tools/prof.py --mib 1024 --kind text,binary,random,mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c1-48
-done > gpurun_out/t13_ab.log 2>&1
-cat gpurun_out/t13_ab.log
+for o in 1 0; do
+  echo "== order $o"
+  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --kind text,binary,random,mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
+  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --chunk 1500 --kind packet --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
+  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --chunk 4096 --kind mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
+  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --chunk 262144 --kind mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
+done > gpurun_out/t14_ab.log 2>&1
+cat gpurun_out/t14_ab.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 300 2>&1 | tail -2

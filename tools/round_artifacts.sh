@@ -2,7 +2,7 @@
 # Everything profiles/ is made from, in one GPU-box call (run from the repo root under gpurun):
 #   tests, both bench arms, the ncu launch list of the bench, one full ncu capture per kernel,
 #   the packets / chunk-size sweep.  Outputs land in gpurun_out/.
-R=${1:-r1}
+R=${1:-r2}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_gpu_tests.log 2>&1; tail -2 gpurun_out/${R}_gpu_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
@@ -17,3 +17,4 @@ for k in k1_match k23_parse_pack k4_decode; do
 done
 timeout 900 python tools/sweep.py > gpurun_out/${R}_sweep.jsonl 2> gpurun_out/${R}_sweep.err; tail -3 gpurun_out/${R}_sweep.jsonl
 ls -la gpurun_out | tail -12
+timeout 600 python tools/inc_device_bench.py --flows 1048576 --sample 256 > gpurun_out/${R}_incremental_device.json 2> gpurun_out/${R}_incremental_device.err; cat gpurun_out/${R}_incremental_device.json
