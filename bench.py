@@ -36,7 +36,7 @@ CPU_SAMPLE_CHUNKS = 2048         # 128 MiB of the same corpus for the CPU legs
 
 def profiled_traffic():
     """DRAM bytes of the dominant kernel (K1) for one launch on this workload, from the committed
-    ncu --set full summary (profiles/r1_k1_match.txt); None if that file is absent."""
+    ncu --set full summary (profiles/r2_k1_match.txt); None if that file is absent."""
     try:
         text = open(os.path.join(ROOT, "profiles", "r1_k1_match.txt")).read()
         gb = float(text.split("dram traffic (read+write):")[1].split("GB")[0])
@@ -307,7 +307,7 @@ def run_gpu_arm(args):
         roof = {"bound": "hbm", "kernel": "k1_match (dominant; followed by k23_parse_pack)",
                 "achieved": alg_bytes_k1 / (t_k1 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes_k1 / (t_k1 * 1e-3) / 1e9 / peak, "traffic": profiled_traffic(),
-                "traffic_source": "ncu --set full, profiles/r1_k1_match.txt (input + 2 B/position of match records)",
+                "traffic_source": "ncu --set full, profiles/r2_k1_match.txt (input + 2 B/position of match records)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_k1,
                 "per_kernel_ms": {"k1_match": t_k1, "k23_parse_pack": t_k23, "k4_decode": t_k4},

@@ -1,10 +1,4 @@
 mkdir -p gpurun_out
-for o in 1 0; do
-  echo "== order $o"
-  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --kind text,binary,random,mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
-  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --chunk 1500 --kind packet --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
-  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --chunk 4096 --kind mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
-  LZS_B200_ORDER=$o timeout 200 python tools/prof.py --mib 1024 --chunk 262144 --kind mixed --iters 3 --time 2>&1 | grep "iter 2" | cut -c70-140
-done > gpurun_out/t14_ab.log 2>&1
-cat gpurun_out/t14_ab.log
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 300 2>&1 | tail -2
+ASAN=$(gcc -print-file-name=libasan.so)
+LD_PRELOAD=$ASAN ASAN_OPTIONS=protect_shadow_gap=0:detect_leaks=0:abort_on_error=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 LZS_B200_LIB=$PWD/variants/asan.so timeout 900 python tools/sanitize.py > gpurun_out/r2_host_asan_ubsan.log 2>&1
+echo "rc=$?"; grep -E "workload|ERROR: AddressSanitizer|runtime error|SUMMARY" gpurun_out/r2_host_asan_ubsan.log | head -12; tail -3 gpurun_out/r2_host_asan_ubsan.log

@@ -34,3 +34,37 @@ assert out == comp[-1]
 back, _ = D.drive(ours, True, comp[-1], 50, 70, 1600)
 assert back == data[-1]
 print("sanitize workload ok")
+# round 2: device-resident flows through the incremental API, the decoder's launch order (>= 1024
+# streams with room in scratch), the pack kernel, the forced exact match-finder launch
+import torch
+flows = 1200
+db = B.DeviceBatch(flows * 1500, 1500)
+db.fill(B.CORPUS_PACKET, 0x5EED0000 + 3)
+db.compress(); db.decompress(); torch.cuda.synchronize()
+assert db.roundtrip_ok()
+dev = torch.device("cuda:0")
+cap = (B.compressed_max(1500) + 15) // 16 * 16
+out = torch.zeros(flows * cap, dtype=torch.uint8, device=dev)
+idx = torch.arange(flows, dtype=torch.int64, device=dev)
+f = B.DeviceFlows(flows)
+full = lambda v: torch.full((flows,), v, dtype=torch.int64, device=dev)
+f.offer(db.raw.data_ptr() + idx * 1500, full(1500), out.data_ptr() + idx * cap, full(cap), True)
+produced = torch.zeros(flows, dtype=torch.int64, device=dev)
+for _ in range(64):
+    _, ou, _ = f.call()
+    produced += ou
+    if bool(((f.jobs[:, 5] >> 32) == 0).all()):
+        break
+assert torch.equal(produced.to(torch.int32), db.comp_len)
+sys.path.insert(0, os.path.join(ROOT, "lzs-compression_b200", "python"))
+import lzs_dist
+packed, poff = lzs_dist.pack_streams(db.comp, db.comp_off, db.comp_len)
+torch.cuda.synchronize()
+B.lib().lzs_b200_set_force_safe_match.argtypes = [ctypes.c_int]
+B.lib().lzs_b200_set_force_safe_match(1)
+small = B.DeviceBatch(40 * 3000, 3000)
+small.fill(B.CORPUS_MIXED, 0x5EED0000 + 9)
+small.compress(); small.decompress(); torch.cuda.synchronize()
+B.lib().lzs_b200_set_force_safe_match(0)
+assert small.roundtrip_ok()
+print("sanitize workload (round 2 additions) ok")
