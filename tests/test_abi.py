@@ -144,3 +144,19 @@ def test_layout_is_validated_before_anything_runs(B):
     rc = call(2048, 4096)
     assert rc in (0, -1), L.lzs_b200_last_error()
     assert L.lzs_b200_release() == 0
+
+
+def test_install_layout_matches_the_reference(tmp_path, B):
+    """`make install` gives the layout of the reference's automake rules
+    (c/src/liblzs/Makefile.am:10-17, liblzs.pc.in:6-10): include/lzs/lzs.h, lib/liblzs.so.4 (+ the
+    liblzs.so link), lib/pkgconfig/liblzs.pc under the name "lzs"."""
+    dest = str(tmp_path / "stage")
+    r = subprocess.run(["make", "-C", os.path.join(helpers.ROOT, "lzs-compression_b200"), "install",
+                        "DESTDIR=" + dest, "PREFIX=/usr"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for rel in ("usr/include/lzs/lzs.h", "usr/include/lzs/lzs_b200.h", "usr/lib/liblzs.so.4", "usr/lib/liblzs.so",
+                "usr/lib/pkgconfig/liblzs.pc", "usr/bin/lzs-b200"):
+        assert os.path.exists(os.path.join(dest, rel)), rel
+    pc = open(os.path.join(dest, "usr/lib/pkgconfig/liblzs.pc")).read()
+    assert "Name: lzs" in pc and "-llzs" in pc and "Version: 0.7.0" in pc
+    assert os.readlink(os.path.join(dest, "usr/lib/liblzs.so")) == "liblzs.so.4"
