@@ -190,6 +190,10 @@ int lzs_b200_release(void);
 
 /* Tuning knobs (also read once from the environment: LZS_B200_DECODE_LANES). */
 int lzs_b200_set_decode_lanes(int lanes_per_stream);   /* 4, 8, 16 or 32 */
+/* Option (also LZS_B200_ZEROCOPY=1): lzs_b200_decompress_batch_host writes straight into an output
+ * buffer that is pinned and device mapped instead of staging it in device memory and copying.
+ * Off by default: measured slightly slower on B200 / PCIe gen 5 (31 vs 29 ms per GiB). */
+int lzs_b200_set_zero_copy_output(int on);
 /* Test knob: run the match finder's exact-for-any-exchange-order launch after every fast launch
  * (normally it returns at once: sm_100a serves the exchanges in the order the fast launch
  * assumes).  Same records, several times slower. */

@@ -442,3 +442,42 @@ def test_host_batches_touch_nothing_outside_the_produced_bytes_slots(B, n_stream
         covered[a:a + int(dec_cap[s])] = True
     assert (back[~covered] == 0x5A).all()
     assert L.lzs_b200_release() == 0
+
+
+def test_decoder_writes_straight_into_pinned_caller_memory(B):
+    """lzs_b200_decompress_batch_host on a pinned (device-mapped) output buffer can decode straight
+    into it over PCIe, no staging copy (an option, lzs_b200_set_zero_copy_output): same bytes, same lengths, and still not a byte outside
+    the produced ranges (sentinels between and inside the slots)."""
+    import ctypes
+    import torch
+    L = B.lib()
+    n = 700
+    rng = np.random.default_rng(77)
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, int(rng.integers(1, 9000)), first_index=i).tobytes() for i in range(n)]
+    packed, off, ln = B.compress_streams_packed(data)
+    cap = np.array([len(d) + 40 for d in data], dtype=np.uint32)          # slots larger than what is produced
+    out_off = np.zeros(n, dtype=np.uint64)
+    pos = 11
+    for s in range(n):
+        out_off[s] = pos
+        pos += int(cap[s]) + 5
+    span = pos
+    pinned = torch.full((span + 64,), 0x3C, dtype=torch.uint8).pin_memory()
+    src = torch.from_numpy(packed.copy()).pin_memory()
+    d_len = np.zeros(n, dtype=np.uint32)
+    u8 = B.u8p
+    L.lzs_b200_set_zero_copy_output.argtypes = [ctypes.c_int]
+    L.lzs_b200_set_zero_copy_output(1)
+    try:
+        B.check(L.lzs_b200_decompress_batch_host(ctypes.cast(src.data_ptr(), u8), B._p(off, B.u64p), B._p(ln, B.u32p),
+                                                 len(packed), ctypes.cast(pinned.data_ptr(), u8), B._p(out_off, B.u64p),
+                                                 B._p(cap, B.u32p), B._p(d_len, B.u32p), span, n))
+    finally:
+        L.lzs_b200_set_zero_copy_output(0)
+    got = pinned.numpy()
+    written = np.zeros(len(got), dtype=bool)
+    for s in range(n):
+        a = int(out_off[s])
+        assert int(d_len[s]) == len(data[s]) and got[a:a + len(data[s])].tobytes() == data[s], s
+        written[a:a + len(data[s])] = True
+    assert (got[~written] == 0x3C).all(), "the decoder wrote outside the bytes it produced"

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-ASAN=$(gcc -print-file-name=libasan.so)
-LD_PRELOAD=$ASAN ASAN_OPTIONS=protect_shadow_gap=0:detect_leaks=0:abort_on_error=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 LZS_B200_LIB=$PWD/variants/asan.so timeout 900 python tools/sanitize.py > gpurun_out/r2_host_asan_ubsan.log 2>&1
-echo "rc=$?"; grep -E "workload|ERROR: AddressSanitizer|runtime error|SUMMARY" gpurun_out/r2_host_asan_ubsan.log | head -12; tail -3 gpurun_out/r2_host_asan_ubsan.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 300 -k "pinned or slots or packed" 2>&1 | tail -3
+for z in 1 0; do echo "== zerocopy $z"; LZS_B200_ZEROCOPY=$z timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-pageable 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['decompress_gbs'], d['e2e'])"; done
+LZS_B200_TRACE=1 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu --no-pageable 2>&1 | grep "trace" | tail -40
