@@ -80,6 +80,28 @@ int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *i
                                             uint32_t *out_len, uint8_t *status, uint32_t n_streams,
                                             void *scratch, size_t scratch_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------
+ * Packets of flows with KEPT HISTORY, the bulk path (RFC 1974 style: the
+ * reference resets neither its compressor's nor its decoder's history at an end marker,
+ * lzs-compression.c:796-820, lzs-decompression.c:564-576).  Stream s is ONE packet; the caller keeps
+ * a flow's packets contiguous in memory, and hist_len[s] (<= 2047, more is clamped) says how many
+ * bytes in front of the packet are the flow's earlier packets.  The packet is compressed exactly as
+ * init-once + lzs_compress_incremental(add_end_marker = true)-until-END_MARKER per packet does it:
+ * matches may reach back into the history, tokens end with the packet, every packet ends with its
+ * own end marker.  Compressing is parallel over ALL packets of ALL flows (one call); decoding is
+ * serial inside a flow -- packet k needs packets < k of its flow decoded, in front of its own output
+ * -- so the decoder is called once per packet index with all flows.  hist_len == NULL or all zero:
+ * the plain batch calls.
+ * ---------------------------------------------------------------------------- */
+int lzs_b200_compress_flows_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                         const uint32_t *hist_len, uint64_t in_span, uint8_t *out,
+                                         const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                                         uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream);
+int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                           uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                           const uint32_t *hist_len, uint32_t *out_len, uint8_t *status,
+                                           uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream);
+
 /* Copies n streams from their slots (src + src_off[s], len[s] bytes) to packed positions
  * (dst + dst_off[s]); both offsets must be multiples of 16 and every slot readable up to the
  * next multiple of 16 of its length.  What the packed host compressor and the multi-GPU gather

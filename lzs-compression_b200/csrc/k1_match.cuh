@@ -120,6 +120,7 @@ constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
 
 struct K1Tile {
     uint32_t sid, t0, tile_n, n, v0;
+    uint32_t skip;      /* the first `skip` positions are kept history of the flow (built into the tables, not matched) */
 };
 
 /* Hash of the k-gram that starts the 12 bytes (w0, w1, w2); (m0, m1, m2) mask the bytes that
@@ -652,7 +653,7 @@ __device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_
         if (c * 32u >= d.tile_n) break;
         if (r < d.tile_n) {
             const uint32_t i = d.t0 + r;
-            mout[i] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
+            if (i >= d.skip) mout[i - d.skip] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
         }
         __syncwarp();
     }
@@ -665,7 +666,7 @@ template <bool kSafe>
 __global__ void __launch_bounds__(kK1Threads, 1)
 k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          const uint32_t *__restrict__ in_len, match_t *__restrict__ matches, uint32_t n_streams,
-         uint32_t *__restrict__ ctl)
+         uint32_t *__restrict__ ctl, const uint32_t *__restrict__ hist_len)
 {
     if (kSafe && *reinterpret_cast<volatile uint32_t *>(ctl + 2) == 0u) return;
     uint32_t *next_stream = ctl + (kSafe ? 1 : 0);
@@ -719,8 +720,16 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             if (lane == 0) sid = atomicAdd(next_stream, 1u);
             sid = __shfl_sync(LZS_FULL_MASK, sid, 0);
             if (sid >= n_streams) break;
-            const uint32_t n = in_len[sid];
-            const uint8_t *src = in + in_off[sid];
+            /* Flows with kept history (RFC 1974 style; the reference does not reset its history at an
+             * end marker, lzs-compression.c:796-820): the hist bytes that precede the packet in memory
+             * are the flow's earlier packets.  They go through the tables like any other position --
+             * the stream the loader and the build warps see starts `hist` bytes early -- and only the
+             * packet's own positions are matched (candidates may reach back into the history, the
+             * look-ahead ends with the packet). */
+            const uint32_t own = in_len[sid];
+            const uint32_t hist = (hist_len != nullptr && own != 0u) ? umin32(hist_len[sid], kWindow) : 0u;
+            const uint32_t n = own + hist;
+            const uint8_t *src = in + in_off[sid] - hist;
             /* last aligned word that holds a byte of the stream (n > 0 inside the tile loop) */
             const uintptr_t wlast = (reinterpret_cast<uintptr_t>(src) + (n ? n - 1u : 0u)) & ~static_cast<uintptr_t>(3);
             const uint32_t v0 = vnext;
@@ -773,7 +782,7 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
 #endif
                 if (lane == 0) {
                     K1Tile d;
-                    d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0;
+                    d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0; d.skip = hist;
                     s_desc[g & 7u] = d;
                     s_qnext[g & 15u] = 0;    /* nobody can still be on tile g - 16 */
                 }

@@ -192,9 +192,10 @@ k23_parse_pack(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
             const uint32_t p = pos + static_cast<uint32_t>(last);
             const uint32_t loff = __shfl_sync(LZS_FULL_MASK, off, last);
             uint32_t       L = kSearchMax;                    /* the first 12 bytes are known to match */
+            const uint8_t *from = src - loff;                 /* may point into the flow's kept history, in front of the packet */
             for (;;) {
                 const uint32_t idx = p + L + lane;
-                const bool     same = (idx < n) && (src[idx] == src[idx - loff]);
+                const bool     same = (idx < n) && (src[idx] == from[idx]);
                 const uint32_t ball = __ballot_sync(LZS_FULL_MASK, same);
                 if (ball == LZS_FULL_MASK) {
                     L += 32u;

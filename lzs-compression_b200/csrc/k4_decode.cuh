@@ -84,7 +84,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
           const uint32_t *__restrict__ in_len, uint8_t *__restrict__ out,
           const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
           uint32_t *__restrict__ out_len, uint32_t n_streams, uint32_t *__restrict__ next_stream,
-          uint8_t *__restrict__ status, const uint32_t *__restrict__ order)
+          uint8_t *__restrict__ status, const uint32_t *__restrict__ order, const uint32_t *__restrict__ hist_len)
 {
     LZS_DYN_SMEM(uint8_t, smem);
     const uint32_t lane = lane_id();
@@ -102,6 +102,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     /* per-stream state; identical in all lanes of a group */
     bool     active = false, exhausted = false, ext = false, vec_ok = false;
     uint32_t sid = 0, cap = 0, pos = 0, flushed = 0, off = 1;
+    int32_t  hist = 0;                                  /* kept history of the flow: bytes before dst that offsets may reach */
     uint32_t cur = 0, end = 0;                          /* bit cursor / end, from word 0      */
     uint32_t fill_hi = 0, nwords = 0, tail = 0;         /* words staged so far; stream extent */
     const uint32_t *wbase = nullptr;
@@ -161,6 +162,13 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     off = 1;
                     ext = false;
                     active = true;
+                    /* Flows with kept history: the decoder of the reference keeps its history across end
+                     * markers (lzs-decompression.c:564-576), so a packet's offsets may reach into the
+                     * flow's earlier packets -- the hist bytes in front of this packet's output, already
+                     * decoded by an earlier launch.  They are loaded into the ring behind position 0. */
+                    hist = hist_len != nullptr ? static_cast<int32_t>(umin32(hist_len[sid], kWindow)) : 0;
+                    for (int32_t k = static_cast<int32_t>(gl); k < hist; k += G)
+                        smem[ring0 + (static_cast<uint32_t>(k - hist) & (kDecRing - 1u))] = dst[k - hist];
                 }
             }
             __syncwarp();
@@ -263,7 +271,7 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     uint32_t kk = k;
                     if (kk >= off) kk = small_mod(kk, off);   /* overlap: periodic extension */
                     const int32_t s = static_cast<int32_t>(pos + kk) - static_cast<int32_t>(off);
-                    if (s >= 0) v[t] = smem[ring0 + (static_cast<uint32_t>(s) & (kDecRing - 1u))];
+                    if (s >= -hist) v[t] = smem[ring0 + (static_cast<uint32_t>(s) & (kDecRing - 1u))];
                 }
             }
             __syncwarp();

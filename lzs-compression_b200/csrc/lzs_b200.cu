@@ -188,8 +188,11 @@ size_t lzs_b200_decompress_scratch_bytes_for(uint32_t n_streams)
     return kCounterBytes + align_up(static_cast<size_t>(n_streams) * sizeof(uint32_t), 256);
 }
 
-int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
-                                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream)
+}  // extern "C"
+
+namespace {
+int match_batch(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, const uint32_t *hist_len,
+                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream)
 {
     if (n_streams == 0) return LZS_B200_OK;
     if (!in || !in_off || !in_len || !matches || !counter) return fail(LZS_B200_EINVAL, "null pointer");
@@ -203,14 +206,44 @@ int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const
     if (g_force_safe_match.load()) CUDA_TRY(cudaMemsetAsync(counter + 2, 1, 1, st));
     const unsigned grid = n_streams < static_cast<uint32_t>(d->sms) ? n_streams : static_cast<unsigned>(d->sms);
     lzs::k1_match<false><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
-                                                                          counter);
+                                                                          counter, hist_len);
     /* the exact-for-any-hardware variant: returns at once unless the fast launch saw an exchange
      * order it does not handle (never on sm_100a); on the stream, so nothing waits on the host */
     lzs::k1_match<true><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
-                                                                         counter);
+                                                                         counter, hist_len);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return LZS_B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int lzs_b200_match_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream)
+{
+    return match_batch(in, in_off, in_len, nullptr, matches, n_streams, counter, stream);
+}
+
+/* Packets of flows with kept history, the bulk path: stream s is ONE packet,
+ * compressed as lzs_compress_incremental(add_end_marker = true) does on a state whose history holds
+ * the hist_len[s] (<= 2047) bytes that PRECEDE in + in_off[s] in memory (the flow's earlier packets,
+ * kept contiguous by the caller).  With hist_len all zero this is lzs_b200_compress_batch_device. */
+int lzs_b200_compress_flows_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                         const uint32_t *hist_len, uint64_t in_span, uint8_t *out,
+                                         const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                                         uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!scratch || scratch_bytes < lzs_b200_compress_scratch_bytes(in_span))
+        return fail(LZS_B200_EINVAL, "scratch too small: need %zu bytes, got %zu",
+                    lzs_b200_compress_scratch_bytes(in_span), scratch_bytes);
+    uint32_t *counter = static_cast<uint32_t *>(scratch);
+    uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(scratch) + kCounterBytes);
+    int rc = match_batch(in, in_off, in_len, hist_len, matches, n_streams, counter, stream);
+    if (rc) return rc;
+    return lzs_b200_parse_pack_batch_device(in, in_off, in_len, matches, out, out_off, out_cap, out_len,
+                                            n_streams, stream);
 }
 
 int lzs_b200_parse_pack_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
@@ -261,6 +294,19 @@ int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *i
                                             uint32_t *out_len, uint8_t *status, uint32_t n_streams,
                                             void *scratch, size_t scratch_bytes, void *stream)
 {
+    return lzs_b200_decompress_flows_batch_device(in, in_off, in_len, out, out_off, out_cap, nullptr, out_len, status,
+                                                  n_streams, scratch, scratch_bytes, stream);
+}
+
+/* Decoder side of the same: packet s is decoded as lzs_decompress_incremental does on a state whose
+ * history holds the hist_len[s] (<= 2047) bytes that precede out + out_off[s] -- the flow's earlier
+ * packets, ALREADY decoded by an earlier launch (a flow is serial: one launch per packet index,
+ * all flows together).  hist_len == NULL: plain independent streams. */
+int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                           uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                           const uint32_t *hist_len, uint32_t *out_len, uint8_t *status,
+                                           uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream)
+{
     if (n_streams == 0) return LZS_B200_OK;
     if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len)
         return fail(LZS_B200_EINVAL, "null pointer");
@@ -292,19 +338,19 @@ int lzs_b200_decompress_status_batch_device(const uint8_t *in, const uint64_t *i
     switch (lanes) {
         case 4:
             lzs::k4_decode<4><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<4>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
             break;
         case 16:
             lzs::k4_decode<16><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<16>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
             break;
         case 32:
             lzs::k4_decode<32><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<32>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
             break;
         default:
             lzs::k4_decode<8><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<8>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order);
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
             break;
     }
     g_launches++;

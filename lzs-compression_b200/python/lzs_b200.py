@@ -365,3 +365,65 @@ class DeviceFlows:
         flag = self.torch.where(done, self.torch.zeros_like(status), (j[:, 5] >> 32) & 1)
         j[:, 5] = flag << 32
         return in_used.clone(), out_used.clone(), status.clone()
+
+
+# ------------------------------------------- flows with kept history, the bulk path
+
+class DeviceFlowTable:
+    """n_flows flows x n_packets packets of plen bytes, a flow's packets contiguous in device memory
+    (plumbing for lzs_b200_compress_flows_batch_device / lzs_b200_decompress_flows_batch_device).
+    compress(): ALL packets of all flows in one call, each with its flow's earlier packets as history;
+    decompress(): one call per packet index (a flow is serial), all flows together."""
+
+    def __init__(self, n_flows, n_packets, plen, device="cuda:0"):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.n_flows, self.n_packets, self.plen = int(n_flows), int(n_packets), int(plen)
+        self.n = self.n_flows * self.n_packets
+        self.flow_bytes = self.n_packets * self.plen
+        self.cap = aligned_stride(compressed_max(self.plen))
+        dev = self.device
+        idx = torch.arange(self.n, dtype=torch.int64, device=dev)          # stream s = flow s // P, packet s % P
+        self.k = idx % self.n_packets
+        self.raw_off = idx * self.plen                                     # flows back to back, packets contiguous
+        self.raw_len = torch.full((self.n,), self.plen, dtype=torch.int32, device=dev)
+        self.hist = torch.clamp(self.k * self.plen, max=2047).to(torch.int32)
+        self.comp_off = idx * self.cap
+        self.comp_cap = torch.full((self.n,), self.cap, dtype=torch.int32, device=dev)
+        self.comp_len = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.dec_len = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        total = self.n * self.plen
+        self.raw = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+        self.comp = torch.zeros(self.n * self.cap + 64, dtype=torch.uint8, device=dev)
+        self.dec = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+        L = lib()
+        vp = ctypes.c_void_p
+        L.lzs_b200_compress_flows_batch_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, vp, vp, vp, ctypes.c_uint32,
+                                                           vp, ctypes.c_size_t, vp]
+        L.lzs_b200_decompress_flows_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp,
+                                                             ctypes.c_size_t, vp]
+        self.scratch = torch.empty(L.lzs_b200_compress_scratch_bytes(total), dtype=torch.uint8, device=dev)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def compress(self, with_history=True):
+        hist = self.hist.data_ptr() if with_history else None
+        check(lib().lzs_b200_compress_flows_batch_device(
+            self.raw.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(), hist, self.n * self.plen,
+            self.comp.data_ptr(), self.comp_off.data_ptr(), self.comp_cap.data_ptr(), self.comp_len.data_ptr(), self.n,
+            self.scratch.data_ptr(), self.scratch.numel(), self._stream()))
+
+    def decompress(self):
+        t = self.torch
+        for k in range(self.n_packets):
+            sel = t.nonzero(self.k == k).flatten()
+            pick = lambda a: a[sel].contiguous()
+            c_off, c_len, o_off, o_cap, h = pick(self.comp_off), pick(self.comp_len), pick(self.raw_off), pick(self.raw_len), pick(self.hist)
+            o_len = t.zeros(sel.numel(), dtype=t.int32, device=self.device)
+            check(lib().lzs_b200_decompress_flows_batch_device(
+                self.comp.data_ptr(), c_off.data_ptr(), c_len.data_ptr(), self.dec.data_ptr(), o_off.data_ptr(),
+                o_cap.data_ptr(), h.data_ptr(), o_len.data_ptr(), None, int(sel.numel()), self.scratch.data_ptr(),
+                self.scratch.numel(), self._stream()))
+            self.dec_len[sel] = o_len

@@ -58,10 +58,44 @@ def decompress(comp, comp_off, comp_len, out_off, out_cap, with_status=False):
     out = torch.empty(span + 64, dtype=torch.uint8, device=comp.device)
     out_len = torch.zeros(max(n, 1), dtype=torch.int32, device=comp.device)
     status = torch.zeros(max(n, 1), dtype=torch.uint8, device=comp.device)
-    scratch = torch.empty(L.lzs_b200_decompress_scratch_bytes(), dtype=torch.uint8, device=comp.device)
+    L.lzs_b200_decompress_scratch_bytes_for.restype = __import__("ctypes").c_size_t
+    L.lzs_b200_decompress_scratch_bytes_for.argtypes = [__import__("ctypes").c_uint32]
+    scratch = torch.empty(L.lzs_b200_decompress_scratch_bytes_for(n), dtype=torch.uint8, device=comp.device)
     _B.check(L.lzs_b200_decompress_status_batch_device(
         comp.data_ptr(), comp_off.data_ptr(), comp_len.data_ptr(), out.data_ptr(), out_off.data_ptr(),
         out_cap.data_ptr(), out_len.data_ptr(), status.data_ptr() if with_status else None, n, scratch.data_ptr(),
         scratch.numel(), torch.cuda.current_stream(comp.device).cuda_stream))
     scratch.record_stream(torch.cuda.current_stream(comp.device))
     return (out, out_len[:n], status[:n]) if with_status else (out, out_len[:n])
+
+
+# ---------------------------------------------------------------- registered operators
+# The same two calls as torch.library custom ops (namespace lzs_b200), so that they show up in
+# torch's dispatcher / profiler / export like any other operator:
+#     comp, comp_off, comp_len = torch.ops.lzs_b200.compress(data, off, length)
+#     out, out_len, status     = torch.ops.lzs_b200.decompress(comp, comp_off, comp_len, out_off, out_cap)
+# CUDA only; there is no CPU kernel behind them (the codec has no CPU path).
+try:
+    @torch.library.custom_op("lzs_b200::compress", mutates_args=(), device_types="cuda")
+    def compress_op(data: torch.Tensor, off: torch.Tensor, length: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        comp, comp_off, comp_len = compress(data, off, length)
+        return comp, comp_off, comp_len.clone()
+
+    @compress_op.register_fake
+    def _(data, off, length):
+        n = off.shape[0]
+        return (data.new_empty(torch.library.get_ctx().new_dynamic_size()), off.new_empty(n), length.new_empty(n))
+
+    @torch.library.custom_op("lzs_b200::decompress", mutates_args=(), device_types="cuda")
+    def decompress_op(comp: torch.Tensor, comp_off: torch.Tensor, comp_len: torch.Tensor, out_off: torch.Tensor,
+                      out_cap: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        out, out_len, status = decompress(comp, comp_off, comp_len, out_off, out_cap, with_status=True)
+        return out, out_len.clone(), status.clone()
+
+    @decompress_op.register_fake
+    def _(comp, comp_off, comp_len, out_off, out_cap):
+        n = comp_off.shape[0]
+        return (comp.new_empty(torch.library.get_ctx().new_dynamic_size()), comp_len.new_empty(n),
+                comp.new_empty(n))
+except (AttributeError, RuntimeError):          # an older torch without torch.library.custom_op
+    compress_op = decompress_op = None

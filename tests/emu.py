@@ -117,3 +117,81 @@ def compress(streams, caps=None, grid=1, align=16, lead=0, out_lead=0):
     lib().emu_parse_pack(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p), _ptr(dst),
                          _ptr(out_off, c_u64p), _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams))
     return _collect(dst, out_off, caps, out_len, "packer")
+
+
+# ---- flows with kept history (lzs_b200_*_flows_batch_device on the emulator) ----
+
+def flows_layout(flows, lead=0):
+    """Packets of a flow contiguous, flows 16-byte aligned (+ lead).  Returns (buf, off, len, hist)."""
+    offs, lens, hist, pos = [], [], [], 0
+    for pk in flows:
+        pos = _align(pos, 16) + lead
+        done = 0
+        for p in pk:
+            offs.append(pos)
+            lens.append(len(p))
+            hist.append(min(2047, done))
+            pos += len(p)
+            done += len(p)
+    buf = np.zeros(_align(pos, 16) + 64, dtype=np.uint8)
+    i = 0
+    for pk in flows:
+        for p in pk:
+            buf[offs[i]:offs[i] + len(p)] = np.frombuffer(bytes(p), dtype=np.uint8)
+            i += 1
+    return buf, np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint32), np.array(hist, dtype=np.uint32)
+
+
+def compress_flows(flows, grid=1, lead=0):
+    """All packets of all flows in one emulated launch; returns a list (per flow) of lists of streams."""
+    L = lib()
+    L.emu_set_hist.argtypes = [c_u32p]
+    src, in_off, in_len, hist = flows_layout(flows, lead)
+    n = len(in_len)
+    m = np.zeros(len(src) + 16, dtype=np.uint16)
+    L.emu_set_hist(_ptr(hist, c_u32p))
+    try:
+        L.emu_match(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p), n, grid)
+    finally:
+        L.emu_set_hist(None)
+    caps = [int(l) + (int(l) + 7) // 8 + 3 for l in in_len]
+    dst, out_off, out_cap = _out_layout(caps, 0)
+    out_len = np.zeros(n, dtype=np.uint32)
+    L.emu_parse_pack(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(m, c_u16p), _ptr(dst),
+                     _ptr(out_off, c_u64p), _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), n)
+    flat = _collect(dst, out_off, caps, out_len, "packer")
+    res, i = [], 0
+    for pk in flows:
+        res.append(flat[i:i + len(pk)])
+        i += len(pk)
+    return res
+
+
+def decode_flows(comp_flows, plain_lens):
+    """Decoder with kept history: one emulated launch per packet index, all flows together."""
+    L = lib()
+    L.emu_decode_hist.argtypes = [c_u8p, c_u64p, c_u32p, c_u8p, c_u64p, c_u32p, c_u32p, ctypes.c_uint32, ctypes.c_uint,
+                                  c_u32p]
+    n_flows = len(comp_flows)
+    starts, pos = [], 0
+    for lens in plain_lens:
+        pos = _align(pos, 16)
+        starts.append(pos)
+        pos += sum(lens)
+    out = np.full(pos + 64, 0xEE, dtype=np.uint8)
+    depth = max(len(c) for c in comp_flows)
+    done = [0] * n_flows
+    for k in range(depth):
+        who = [f for f in range(n_flows) if k < len(comp_flows[f])]
+        streams = [comp_flows[f][k] for f in who]
+        src, in_off, in_len = pack_streams(streams)
+        out_off = np.array([starts[f] + done[f] for f in who], dtype=np.uint64)
+        out_cap = np.array([plain_lens[f][k] for f in who], dtype=np.uint32)
+        hist = np.array([min(2047, done[f]) for f in who], dtype=np.uint32)
+        out_len = np.zeros(len(who), dtype=np.uint32)
+        L.emu_decode_hist(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(out), _ptr(out_off, c_u64p),
+                          _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(who), 2, _ptr(hist, c_u32p))
+        for f, l in zip(who, out_len):
+            assert int(l) == plain_lens[f][k], (f, k, int(l))
+            done[f] += int(l)
+    return [out[starts[f]:starts[f] + sum(plain_lens[f])].tobytes() for f in range(n_flows)]

@@ -12,11 +12,11 @@
 template <int G>
 static void run_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                        const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
-                       unsigned grid, uint8_t *status)
+                       unsigned grid, uint8_t *status, const uint32_t *hist = nullptr)
 {
     uint32_t counter = 0;
     simt::launch(dim3(grid), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<G>(), [&] {
-        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter, status, nullptr);
+        lzs::k4_decode<G>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &counter, status, nullptr, hist);
     });
 }
 
@@ -34,6 +34,17 @@ extern "C" int emu_decode(const uint8_t *in, const uint64_t *in_off, const uint3
     return 0;
 }
 
+static const uint32_t *g_emu_hist = nullptr;   /* kept-history lengths for the next emu_match / emu_decode (test knob) */
+extern "C" void emu_set_hist(const uint32_t *hist) { g_emu_hist = hist; }
+
+extern "C" int emu_decode_hist(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                               const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
+                               unsigned grid, const uint32_t *hist)
+{
+    run_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, grid, nullptr, hist);
+    return 0;
+}
+
 extern "C" int emu_match(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                          uint16_t *matches, uint32_t n, unsigned grid)
 {
@@ -41,10 +52,10 @@ extern "C" int emu_match(const uint8_t *in, const uint64_t *in_off, const uint32
      * fast one recorded an exchange order it does not handle).  Returns that record. */
     uint32_t ctl[4] = {0, 0, 0, 0};
     simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
-        lzs::k1_match<false>(in, in_off, in_len, matches, n, ctl);
+        lzs::k1_match<false>(in, in_off, in_len, matches, n, ctl, g_emu_hist);
     });
     simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
-        lzs::k1_match<true>(in, in_off, in_len, matches, n, ctl);
+        lzs::k1_match<true>(in, in_off, in_len, matches, n, ctl, g_emu_hist);
     });
     return static_cast<int>(ctl[2]);
 }

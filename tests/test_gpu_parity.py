@@ -481,3 +481,35 @@ def test_decoder_writes_straight_into_pinned_caller_memory(B):
         assert int(d_len[s]) == len(data[s]) and got[a:a + len(data[s])].tobytes() == data[s], s
         written[a:a + len(data[s])] = True
     assert (got[~written] == 0x3C).all(), "the decoder wrote outside the bytes it produced"
+
+
+def test_registered_torch_operators():
+    """torch.ops.lzs_b200.compress / decompress (torch.library custom ops over the same device entry
+    points): same bytes as the oracle, status words from the decoder."""
+    import torch
+    from gpu_common import torch_front_end
+    T = torch_front_end()
+    if T.compress_op is None:
+        pytest.skip("this torch has no torch.library.custom_op")
+    o = helpers.oracle()
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, n, first_index=i).tobytes() for i, n in enumerate([1, 700, 4096, 65536, 33])]
+    off, pos = [], 0
+    for d in data:
+        off.append(pos)
+        pos += (len(d) + 15) // 16 * 16
+    buf = torch.zeros(pos + 64, dtype=torch.uint8)
+    for a, d in zip(off, data):
+        buf[a:a + len(d)] = torch.frombuffer(bytearray(d), dtype=torch.uint8)
+    dev = torch.device("cuda:0")
+    t_off = torch.tensor(off, dtype=torch.int64, device=dev)
+    t_len = torch.tensor([len(d) for d in data], dtype=torch.int32, device=dev)
+    comp, comp_off, comp_len = torch.ops.lzs_b200.compress(buf.to(dev), t_off, t_len)
+    torch.cuda.synchronize()
+    c, co, cl = comp.cpu().numpy(), comp_off.cpu().numpy(), comp_len.cpu().numpy()
+    assert [c[int(a):int(a) + int(l)].tobytes() for a, l in zip(co, cl)] == [o.compress(d) for d in data]
+    out, out_len, status = torch.ops.lzs_b200.decompress(comp, comp_off, comp_len, t_off, t_len)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert [got[a:a + len(d)].tobytes() for a, d in zip(off, data)] == data
+    assert out_len.cpu().tolist() == [len(d) for d in data]
+    assert all(s in (0x04, 0x08) for s in status.cpu().tolist())      # end marker seen, or capacity reached exactly at it

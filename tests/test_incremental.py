@@ -264,3 +264,118 @@ def test_gpu_device_resident_flows_through_the_incremental_api():
     if os.path.exists(helpers.REF_SO):
         assert line["call_traces_equal_to_reference"] == 96 and line["second_packet_on_kept_history_checked"] == 64
     assert line["ratio_second_packet_kept_history"] > line["ratio_first_packet"]
+
+
+def _reference_flows(flows, cap=4096):
+    """Every flow through ONE reference compressor state: each packet to its END_MARKER, history kept."""
+    R = _ref()
+    ref = D.StructCodec(R)
+    want = []
+    for pk in flows:
+        st = ref.new(False)
+        outs = []
+        for p in pk:
+            src = np.frombuffer(bytes(p) + b"\0" * 16, dtype=np.uint8).copy()
+            dst = np.zeros(cap, dtype=np.uint8)
+            f = (ctypes.c_uint64 * 4).from_address(ctypes.addressof(st))
+            f[0], f[1], f[2], f[3] = src.ctypes.data, dst.ctypes.data, len(p), cap
+            for _ in range(64):
+                R.lzs_compress_incremental(st, True)
+                if ctypes.c_uint8.from_address(ctypes.addressof(st) + 32).value & D.END_MARKER:
+                    break
+            else:
+                raise AssertionError("reference never reached END_MARKER")
+            outs.append(dst[:cap - f[3]].tobytes())
+        want.append(outs)
+    return want
+
+
+def _test_flows(seed=5, n_flows=7, n_packets=6):
+    rng = np.random.default_rng(seed)
+    vocab = helpers.corpus(helpers.CORPUS_TEXT, 1, 6000, seed=0x5EED0000 + 12).tobytes()
+    recs = helpers.corpus(helpers.CORPUS_BINARY, 1, 6000, seed=0x5EED0000 + 13).tobytes()
+    flows = []
+    for f in range(n_flows):
+        pk = []
+        for k in range(n_packets):
+            base = vocab if (f + k) % 3 else recs
+            a = int(rng.integers(0, 3500)); ln = int(rng.integers(1, 1600))
+            pk.append(base[a:a + ln] + bytes(rng.integers(0, 256, int(rng.integers(0, 9)), dtype=np.uint8)))
+        flows.append(pk)
+    flows.append([b"a", b"", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"a" * 3000, b"ab"])      # runs across packet borders, an empty packet
+    return flows
+
+
+def test_emulated_bulk_path_for_flows_with_kept_history():
+    """lzs_b200_compress_flows_batch_device / lzs_b200_decompress_flows_batch_device (the K1-class path
+    for SURVEY.md section 8f-2) on the emulator: every packet of every flow, compressed in ONE launch
+    with the flow's earlier packets as history, equals what the unmodified reference produces through
+    one compressor state per flow (init once, each packet to its end marker); and the decoder with
+    kept history gives the packets back, one launch per packet index."""
+    flows = _test_flows()
+    want = _reference_flows(flows)
+    got = emu.compress_flows(flows, lead=3)
+    for f, (g, w) in enumerate(zip(got, want)):
+        assert g == w, f
+    # later packets really use the history: smaller than the same packets compressed alone
+    o = helpers.oracle()
+    assert sum(len(c) for c in got[0][1:]) < sum(len(o.compress(p)) for p in flows[0][1:])
+    back = emu.decode_flows(got, [[len(p) for p in pk] for pk in flows])
+    assert back == [b"".join(pk) for pk in flows]
+
+
+@pytest.mark.gpu
+def test_gpu_bulk_path_for_flows_with_kept_history():
+    """The same on the GPU through the C ABI, plus a table of equal-size packets: every packet of a
+    sample of flows against the unmodified reference's one-state-per-flow output, the whole table
+    through the decoder with kept history (one launch per packet index) back to the input."""
+    import torch
+    B = binding()
+    L = B.lib()
+    dev = torch.device("cuda:0")
+    # (1) ragged flows against the reference
+    flows = _test_flows(seed=9, n_flows=40, n_packets=5)
+    want = _reference_flows(flows)
+    src, in_off, in_len, hist = emu.flows_layout(flows, lead=0)
+    n = len(in_len)
+    caps = np.array([helpers.compressed_max(int(l)) for l in in_len], dtype=np.uint32)
+    out_off, _, out_span = B.layout([int(c) for c in caps])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64 if a.dtype == np.uint64 else
+                                                               (np.int32 if a.dtype == np.uint32 else np.uint8))).to(dev)
+    d_src, d_inoff, d_inlen, d_hist, d_outoff, d_outcap = t(src), t(in_off), t(in_len), t(hist), t(out_off), t(caps)
+    d_out = torch.zeros(out_span + 64, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    scratch = torch.empty(L.lzs_b200_compress_scratch_bytes(len(src)), dtype=torch.uint8, device=dev)
+    vp = ctypes.c_void_p
+    L.lzs_b200_compress_flows_batch_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, vp, vp, vp, ctypes.c_uint32, vp,
+                                                       ctypes.c_size_t, vp]
+    B.check(L.lzs_b200_compress_flows_batch_device(d_src.data_ptr(), d_inoff.data_ptr(), d_inlen.data_ptr(), d_hist.data_ptr(),
+                                                   len(src), d_out.data_ptr(), d_outoff.data_ptr(), d_outcap.data_ptr(),
+                                                   d_len.data_ptr(), n, scratch.data_ptr(), scratch.numel(), None))
+    torch.cuda.synchronize()
+    out, lens = d_out.cpu().numpy(), d_len.cpu().numpy()
+    i = 0
+    for f, pk in enumerate(flows):
+        for k in range(len(pk)):
+            a = int(out_off[i])
+            assert out[a:a + int(lens[i])].tobytes() == want[f][k], (f, k)
+            i += 1
+    # (2) a table of flows: sample against the reference, everything through the decoder
+    tab = B.DeviceFlowTable(3000, 4, 1500)
+    B.check(L.lzs_b200_corpus_fill_device(tab.raw.data_ptr(), 1500, 1500, 0, tab.n, 0x5EED0000 + 3, B.CORPUS_PACKET, None))
+    tab.compress()
+    tab.decompress()
+    torch.cuda.synchronize()
+    assert torch.equal(tab.dec[:tab.n * 1500], tab.raw[:tab.n * 1500]) and bool((tab.dec_len == 1500).all())
+    raw = tab.raw[:16 * 4 * 1500].cpu().numpy()
+    sample = [[raw[(f * 4 + k) * 1500:(f * 4 + k + 1) * 1500].tobytes() for k in range(4)] for f in range(16)]
+    want = _reference_flows(sample)
+    comp, clen = tab.comp[:16 * 4 * tab.cap].cpu().numpy(), tab.comp_len[:64].cpu().numpy()
+    for f in range(16):
+        for k in range(4):
+            s = f * 4 + k
+            assert comp[s * tab.cap:s * tab.cap + int(clen[s])].tobytes() == want[f][k], (f, k)
+    with_hist = int(tab.comp_len.sum())
+    tab.compress(with_history=False)
+    torch.cuda.synchronize()
+    assert with_hist < int(tab.comp_len.sum()), "kept history should make later packets smaller"
