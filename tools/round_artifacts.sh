@@ -18,3 +18,4 @@ done
 timeout 900 python tools/sweep.py > gpurun_out/${R}_sweep.jsonl 2> gpurun_out/${R}_sweep.err; tail -3 gpurun_out/${R}_sweep.jsonl
 ls -la gpurun_out | tail -12
 timeout 600 python tools/inc_device_bench.py --flows 1048576 --sample 256 > gpurun_out/${R}_incremental_device.json 2> gpurun_out/${R}_incremental_device.err; cat gpurun_out/${R}_incremental_device.json
+timeout 300 python tools/flows_bench.py > gpurun_out/${R}_flows_bulk.json 2> gpurun_out/${R}_flows_bulk.err; cat gpurun_out/${R}_flows_bulk.json
