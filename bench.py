@@ -182,6 +182,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads to the CPUs NVML names as closest to its GPU, so that the pinned host
+    buffers of the end-to-end leg are allocated (first touch) on that NUMA node and the ranks of one
+    box do not all stage through node 0.  Best effort: returns what was done for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return "nvml ideal cpus: %d of %d allowed (%d..%d)" % (len(after), before, after[0], after[-1])
+    except Exception as e:                                  # no NVML, a cpuset that excludes them, ...
+        return "unchanged (%s)" % type(e).__name__
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -194,6 +210,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the LZS codec has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -327,7 +344,7 @@ def run_gpu_arm(args):
             line["e2e"] = {"value": job_bytes / (t_e2e * 1e-3) / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "steps": e2e["steps"], "api": "lzs_b200_compress_packed_host + lzs_b200_decompress_batch_host",
-                           "host_buffers": "pinned",
+                           "host_buffers": "pinned", "cpu_affinity": affinity,
                            # the same bytes over PCIe in the same order with no kernel at all: the ceiling of this box
                            "copy_only": {"value": job_bytes / (t_copy * 1e-3) / 1e9, "unit": "GB/s", "ms": t_copy,
                                          "what": "H2D input, D2H packed streams, then H2D packed streams, D2H output; "
