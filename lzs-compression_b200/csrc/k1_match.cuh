@@ -73,6 +73,15 @@ constexpr uint32_t kK1WMirror = 64;         /* the first grams again behind the 
 #ifndef LZS_K1_TILE
 #define LZS_K1_TILE 448
 #endif
+#ifndef LZS_K1_FAKE_BUILD_WARPS
+#define LZS_K1_FAKE_BUILD_WARPS 99          /* timing experiments only: build warps from this index on do nothing (wrong results) */
+#endif
+#ifndef LZS_K1_FAKE_LOADER_GRAMS
+#define LZS_K1_FAKE_LOADER_GRAMS 4          /* timing experiments only: < 4 leaves grams unwritten (wrong results) */
+#endif
+#ifndef LZS_K1_LAG
+#define LZS_K1_LAG 0                        /* 1: a batch's links are made one batch later (two batches of exchanges in flight) */
+#endif
 #ifndef LZS_K1_EAGER
 #define LZS_K1_EAGER 0                      /* 1: a query step loads the candidate's bytes together with its link entry */
 #endif
@@ -117,6 +126,32 @@ constexpr uint32_t kK1Ahead = 40;           /* grams filled beyond the tile bein
 static_assert(kWindow + (kK1Depth + 2) * (kK1Tile + kK1StreamGap) + 16 + kK1Ahead < kK1WRing, "gram ring: window + the tiles in the pipeline + those the loader may be ahead");
 
 constexpr uint32_t kK1EndOfWork = 0xFFFFFFFFu;
+
+#if defined(LZS_K1_TIMELINE) && !defined(LZS_SIMT_EMU)
+/* Debug builds only (tools/k1_timeline.py): per tile of CTA 0, when each role started and finished it
+ * (SM clock).  [tile][0] loader may start (ring space free), [1] loader published, [2] first build warp
+ * starts, [3] last build warp starts, [4] first build warp done, [5] last build warp done, [6] first
+ * query warp enters, [7] last query warp leaves. */
+constexpr uint32_t kTlTiles = 8192;
+__device__ unsigned long long g_k1_timeline[kTlTiles][8];
+__device__ unsigned long long g_k1_warp_busy[64][2];      /* per warp of CTA 0: cycles spent building / waiting, summed over tiles */
+__device__ __forceinline__ void tl_set(uint32_t g, int k)
+{
+    if (blockIdx.x == 0 && g < kTlTiles && lane_id() == 0) g_k1_timeline[g][k] = clock64();
+}
+__device__ __forceinline__ void tl_min(uint32_t g, int k)
+{
+    if (blockIdx.x == 0 && g < kTlTiles && lane_id() == 0) atomicMin(&g_k1_timeline[g][k], static_cast<unsigned long long>(clock64()));
+}
+__device__ __forceinline__ void tl_max(uint32_t g, int k)
+{
+    if (blockIdx.x == 0 && g < kTlTiles && lane_id() == 0) atomicMax(&g_k1_timeline[g][k], static_cast<unsigned long long>(clock64()));
+}
+#else
+#define tl_set(g, k) ((void)0)
+#define tl_min(g, k) ((void)0)
+#define tl_max(g, k) ((void)0)
+#endif
 
 struct K1Tile {
     uint32_t sid, t0, tile_n, n, v0;
@@ -288,6 +323,63 @@ __device__ __forceinline__ uint32_t k1_build_group(uint32_t *heads, uint16_t *li
 #pragma unroll
         for (int l = 1; l < NL; l++) h[l] = k1_hash_roll(K0 + l, h[l - 1], w0, w1, w2);
     }
+#if LZS_K1_LAG
+    if (!kSafe) {
+        /* One batch further: the results of a batch's exchanges are turned into links only after the
+         * NEXT batch's exchanges have been issued (and the batch after that hashed), so two batches
+         * of exchanges are in flight and nothing in the loop waits for a round trip. */
+        uint32_t  p_old[NL], p_tag[NL], p_pos = 0;
+        uint16_t *p_lk = lk0;
+        bool      pending = false;
+#pragma unroll
+        for (int l = 0; l < NL; l++) p_old[l] = p_tag[l] = 0;
+#pragma unroll 2
+        for (uint32_t b = 0; b < tile_n; b += 32) {
+            const uint32_t vb = vt + b;
+            const uint32_t pos = vb | lane;
+            uint32_t       old[NL], tagbits[NL];
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                old[l] = smem_exch(hd + l * kK1Slots + (h[l] >> kSlotShift), pos);
+                tagbits[l] = (h[l] >> 5) & 0xF800u;
+            }
+            {
+                const uint32_t x = (vb + 32u) & (kK1WRing - 1);
+                const uint32_t w0 = Wl[x], w1 = Wl[x + 4], w2 = Wl[x + 8];
+                h[0] = k1_hash_start(K0, w0, w1, w2);
+#pragma unroll
+                for (int l = 1; l < NL; l++) h[l] = k1_hash_roll(K0 + l, h[l - 1], w0, w1, w2);
+            }
+            if (pending) {
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    const uint32_t dist = p_pos - p_old[l];
+                    disorder |= dist;
+                    uint32_t e = p_tag[l];
+                    if (dist <= kWindow) e |= dist;
+                    p_lk[l * kK1LinkRing] = static_cast<uint16_t>(e);
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < NL; l++) { p_old[l] = old[l]; p_tag[l] = tagbits[l]; }
+            p_pos = pos;
+            p_lk = lk0 + (vb & (kK1LinkRing - 1));
+            pending = true;
+            __syncwarp();
+        }
+        if (pending) {
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const uint32_t dist = p_pos - p_old[l];
+                disorder |= dist;
+                uint32_t e = p_tag[l];
+                if (dist <= kWindow) e |= dist;
+                p_lk[l * kK1LinkRing] = static_cast<uint16_t>(e);
+            }
+        }
+        return disorder >> 31;
+    }
+#endif
 #pragma unroll 2
     for (uint32_t b = 0; b < tile_n; b += 32) {
         const uint32_t vb = vt + b;                       /* warp-uniform, a multiple of 32 */
@@ -338,26 +430,27 @@ __device__ __forceinline__ void k1_build_runs(uint16_t *runs, const uint32_t *W,
     const uint32_t  vt = v0 + t0;                         /* a multiple of 32 */
     const uint32_t *Wl = W + lane;
     uint16_t       *rl = runs + lane;
-    /* carried from batch to batch in registers: the byte before the batch and how far back its run starts */
-    uint32_t prev_byte = (t0 == 0) ? 0x100u : (W[(vt - 1u) & (kK1WRing - 1)] & 0xFFu);
+    /* carried from batch to batch in a register: how far back the run of the batch's last byte starts.
+     * The byte in front of every position comes from the gram ring (the gram one position back), so
+     * the only thing a batch waits for from the batch before it is that one number. */
     uint32_t carry = (t0 == 0) ? 0u : (runs[(vt - 1u) & (kK1LinkRing - 1)] & kRunBackMask);
-#pragma unroll 1
+#pragma unroll 2
     for (uint32_t b = 0; b < tile_n; b += 32) {
         const uint32_t vb = vt + b;
         const uint32_t x = vb & (kK1WRing - 1);
         const uint32_t w0 = Wl[x], w1 = Wl[x + 4], w2 = Wl[x + 8];
+        const uint32_t wb = W[(vb + lane - 1u) & (kK1WRing - 1)];              /* the gram that starts one byte earlier */
         const uint32_t byte = w0 & 0xFFu;
         const uint32_t rep = byte * 0x01010101u;
         const uint32_t fwd = lcp12(w0, w1, w2, rep, rep, rep);                 /* 1..12 */
-        uint32_t       before = __shfl_up_sync(LZS_FULL_MASK, byte, 1);
-        if (lane == 0) before = prev_byte;
-        const uint32_t starts = __ballot_sync(LZS_FULL_MASK, before != byte);  /* positions that begin a run */
+        /* a stream's first position starts a run whatever lies in front of it in the ring */
+        const bool     start = (t0 + b + lane == 0u) || ((wb & 0xFFu) != byte);
+        const uint32_t starts = __ballot_sync(LZS_FULL_MASK, start);           /* positions that begin a run */
         const uint32_t below = starts & ((2u << lane) - 1u);                   /* starts at or below my lane */
         const uint32_t back = below ? lane - (31u - static_cast<uint32_t>(__clz(static_cast<int>(below))))
                                     : umin32(carry + lane + 1u, kRunBackMask);  /* the run began in an earlier batch */
         rl[vb & (kK1LinkRing - 1)] = static_cast<uint16_t>((fwd << 12) | back);
         carry = __shfl_sync(LZS_FULL_MASK, back, 31);
-        prev_byte = __shfl_sync(LZS_FULL_MASK, byte, 31);
     }
 }
 
@@ -550,7 +643,7 @@ __device__ __forceinline__ void k1_store_grams(const K1Words &r, uint32_t *W, co
         const uint32_t x2 = lane >= 30u ? n2 : d2;
         const uint32_t q0 = p_lo + static_cast<uint32_t>(k) * 128u + 4u * lane;
 #pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
+        for (uint32_t j = 0; j < LZS_K1_FAKE_LOADER_GRAMS; j++) {
             const uint32_t o = m + j;                     /* byte offset from word l: 0..6 */
             const uint32_t g = __funnelshift_r(o < 4u ? x0 : x1, o < 4u ? x1 : x2, (o & 3u) * 8u);
             const uint32_t q = q0 + j;
@@ -771,6 +864,7 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         spin_pause();
                     __threadfence_block();
                 }
+                tl_set(g, 0);
 #if LZS_K1_BULK
                 mbar_wait(&s_stage_bar[stage_n & 1u], (stage_n >> 1) & 1u);
                 k1_store_grams_staged(s_stage[stage_n & 1u], cur, W, src, v0, p_lo, p_hi, n);
@@ -789,6 +883,7 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&s_filled) = g + 1u;
+                tl_set(g, 1);
             }
         }
         if (g > kK1Depth) {
@@ -819,7 +914,12 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             const K1Tile d = s_desc[g & 7u];
             /* the query warps must have left the tile that used this stage before (tile g - depth) */
             if (g >= kK1Depth) mbar_wait(&s_empty[buf], (g / kK1Depth - 1u) & 1u);
-            if (d.sid != kK1EndOfWork) {
+            tl_min(g, 2);
+            tl_max(g, 3);
+#if defined(LZS_K1_TIMELINE) && !defined(LZS_SIMT_EMU)
+            const long long tb0 = clock64();
+#endif
+            if (d.sid != kK1EndOfWork && warp < static_cast<uint32_t>(LZS_K1_FAKE_BUILD_WARPS)) {
                 const uint32_t vt = d.v0 + d.t0;
                 if (kK1Lpw > 1 || kK1Grouped)
                     disorder |= k1_build_tile<kSafe>(warp, heads, links, runs, W, d);
@@ -829,6 +929,11 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 else
                     k1_build_runs(runs, W, d.v0, d.t0, d.tile_n);
             }
+            tl_min(g, 4);
+            tl_max(g, 5);
+#if defined(LZS_K1_TIMELINE) && !defined(LZS_SIMT_EMU)
+            if (blockIdx.x == 0 && lane == 0) g_k1_warp_busy[warp][0] += static_cast<unsigned long long>(clock64() - tb0);
+#endif
             mbar_arrive(&s_full[buf]);
             if (d.sid == kK1EndOfWork) break;
         }
@@ -840,7 +945,9 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             mbar_wait(&s_full[buf], (g / kK1Depth) & 1u);
             const K1Tile d = s_desc[g & 7u];
             if (d.sid == kK1EndOfWork) break;
+            tl_min(g, 6);
             k1_query_chunks(d, &s_qnext[g & 15u], links, runs, W, matches + in_off[d.sid]);
+            tl_max(g, 7);
             mbar_arrive(&s_empty[buf]);
             __syncwarp();
             if (lane == 0) atomicAdd(&s_qdone[buf], 1u);  /* the loader may reuse the ring behind us */

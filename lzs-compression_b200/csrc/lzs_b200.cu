@@ -163,6 +163,28 @@ int lzs_b200_set_decode_lanes(int lanes)
     return LZS_B200_OK;
 }
 
+#ifdef LZS_K1_TIMELINE
+/* debug builds only: reset / fetch the per-tile timeline of K1's CTA 0 (tools/k1_timeline.py) */
+int lzs_b200_debug_timeline(unsigned long long *dst, int reset)
+{
+    static std::vector<unsigned long long> init;
+    const size_t n = static_cast<size_t>(lzs::kTlTiles) * 8;
+    if (reset) {
+        init.assign(n, 0ull);
+        for (size_t i = 0; i < n; i++)
+            if ((i & 7) == 2 || (i & 7) == 4 || (i & 7) == 6) init[i] = ~0ull;      /* the atomicMin slots */
+        return cudaMemcpyToSymbol(lzs::g_k1_timeline, init.data(), n * 8) == cudaSuccess ? 0 : -2;
+    }
+    return cudaMemcpyFromSymbol(dst, lzs::g_k1_timeline, n * 8) == cudaSuccess ? 0 : -2;
+}
+int lzs_b200_debug_warp_busy(unsigned long long *dst, int reset)
+{
+    static unsigned long long zero[128];
+    if (reset) return cudaMemcpyToSymbol(lzs::g_k1_warp_busy, zero, sizeof zero) == cudaSuccess ? 0 : -2;
+    return cudaMemcpyFromSymbol(dst, lzs::g_k1_warp_busy, 128 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int lzs_b200_set_zero_copy_output(int on)
 {
     g_zero_copy_out.store(on ? 1 : 0);

@@ -1,3 +1,3 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 2>&1 | tail -4
-timeout 300 python tools/flows_bench.py > gpurun_out/r2_flows_bulk.json 2> gpurun_out/r2_flows_bulk.err; tail -3 gpurun_out/r2_flows_bulk.err; cat gpurun_out/r2_flows_bulk.json
+for v in q8 q12; do
+  echo "== $v"; LZS_B200_LIB=$PWD/variants/$v.so timeout 200 python tools/k1_time_only.py random,text 2>&1 | tail -2
+done
