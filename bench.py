@@ -210,6 +210,7 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the LZS codec has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
     affinity = bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
@@ -358,6 +359,7 @@ def run_gpu_arm(args):
             line["gather"] = gather
             line["value_with_gather"] = job_bytes / ((t_total + t_gather) * 1e-3) / 1e9
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)              # the CPU leg gets every core the process was given
             line["cpu_baseline"] = cpu_baseline_leg(db)
             line["parity"] = line["cpu_baseline"].pop("parity")
         print(json.dumps(line))

@@ -1,3 +1,4 @@
-for v in q8 q12; do
-  echo "== $v"; LZS_B200_LIB=$PWD/variants/$v.so timeout 200 python tools/k1_time_only.py random,text 2>&1 | tail -2
-done
+timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value',d['value'],'per kernel',d['roofline']['per_kernel_ms'],'e2e',d['e2e']['value'],'parity',d['parity']['mismatches'])"
