@@ -101,6 +101,15 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
                                            uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
                                            const uint32_t *hist_len, uint32_t *out_len, uint8_t *status,
                                            uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream);
+/* A table of flows whose packets have seg_len[f] bytes each (the last of a flow may be shorter): the match
+ * finder takes flow f (in + flow_off[f], flow_len[f] bytes) as ONE stream and ends every position's
+ * look-ahead with its packet, so a flow's bytes go through the tables once; the parse/pack kernel takes the
+ * n_packets packets (pkt_off / pkt_len, each inside a flow) one by one.  Same bytes as the call above. */
+int lzs_b200_compress_flow_table_device(const uint8_t *in, const uint64_t *flow_off, const uint32_t *flow_len,
+                                        const uint32_t *seg_len, uint32_t n_flows, const uint64_t *pkt_off,
+                                        const uint32_t *pkt_len, uint32_t n_packets, uint64_t in_span, uint8_t *out,
+                                        const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                                        void *scratch, size_t scratch_bytes, void *stream);
 
 /* Copies n streams from their slots (src + src_off[s], len[s] bytes) to packed positions
  * (dst + dst_off[s]); both offsets must be multiples of 16 and every slot readable up to the

@@ -156,6 +156,7 @@ __device__ __forceinline__ void tl_max(uint32_t g, int k)
 struct K1Tile {
     uint32_t sid, t0, tile_n, n, v0;
     uint32_t skip;      /* the first `skip` positions are kept history of the flow (built into the tables, not matched) */
+    uint32_t seg;       /* 0, or the stream is a flow of packets of this many bytes: tokens end with the packet */
 };
 
 /* Hash of the k-gram that starts the 12 bytes (w0, w1, w2); (m0, m1, m2) mask the bytes that
@@ -746,7 +747,10 @@ __device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_
         if (c * 32u >= d.tile_n) break;
         if (r < d.tile_n) {
             const uint32_t i = d.t0 + r;
-            if (i >= d.skip) mout[i - d.skip] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, d.n));
+            /* a flow of equal packets as ONE stream: the look-ahead ends with the packet position i lies in
+             * (what the reference does when a packet is flushed with add_end_marker), the history does not */
+            const uint32_t n_eff = d.seg ? umin32(d.n, (i / d.seg + 1u) * d.seg) : d.n;
+            if (i >= d.skip) mout[i - d.skip] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, n_eff));
         }
         __syncwarp();
     }
@@ -759,7 +763,7 @@ template <bool kSafe>
 __global__ void __launch_bounds__(kK1Threads, 1)
 k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          const uint32_t *__restrict__ in_len, match_t *__restrict__ matches, uint32_t n_streams,
-         uint32_t *__restrict__ ctl, const uint32_t *__restrict__ hist_len)
+         uint32_t *__restrict__ ctl, const uint32_t *__restrict__ hist_len, const uint32_t *__restrict__ seg_len)
 {
     if (kSafe && *reinterpret_cast<volatile uint32_t *>(ctl + 2) == 0u) return;
     uint32_t *next_stream = ctl + (kSafe ? 1 : 0);
@@ -877,6 +881,7 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                 if (lane == 0) {
                     K1Tile d;
                     d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0; d.skip = hist;
+                    d.seg = seg_len != nullptr ? seg_len[sid] : 0u;
                     s_desc[g & 7u] = d;
                     s_qnext[g & 15u] = 0;    /* nobody can still be on tile g - 16 */
                 }

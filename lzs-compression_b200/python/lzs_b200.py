@@ -404,9 +404,23 @@ class DeviceFlowTable:
         L.lzs_b200_decompress_flows_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp,
                                                              ctypes.c_size_t, vp]
         self.scratch = torch.empty(L.lzs_b200_compress_scratch_bytes(total), dtype=torch.uint8, device=dev)
+        L.lzs_b200_compress_flow_table_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, vp, vp, ctypes.c_uint32,
+                                                          ctypes.c_uint64, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        fidx = torch.arange(self.n_flows, dtype=torch.int64, device=dev)
+        self.flow_off = fidx * self.flow_bytes
+        self.flow_len = torch.full((self.n_flows,), self.flow_bytes, dtype=torch.int32, device=dev)
+        self.seg_len = torch.full((self.n_flows,), self.plen, dtype=torch.int32, device=dev)
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def compress_table(self):
+        """Every flow as ONE stream for the match finder (the look-ahead ends with each packet)."""
+        check(lib().lzs_b200_compress_flow_table_device(
+            self.raw.data_ptr(), self.flow_off.data_ptr(), self.flow_len.data_ptr(), self.seg_len.data_ptr(), self.n_flows,
+            self.raw_off.data_ptr(), self.raw_len.data_ptr(), self.n, self.n * self.plen, self.comp.data_ptr(),
+            self.comp_off.data_ptr(), self.comp_cap.data_ptr(), self.comp_len.data_ptr(), self.scratch.data_ptr(),
+            self.scratch.numel(), self._stream()))
 
     def compress(self, with_history=True):
         hist = self.hist.data_ptr() if with_history else None

@@ -195,3 +195,36 @@ def decode_flows(comp_flows, plain_lens):
             assert int(l) == plain_lens[f][k], (f, k, int(l))
             done[f] += int(l)
     return [out[starts[f]:starts[f] + sum(plain_lens[f])].tobytes() for f in range(n_flows)]
+
+
+def compress_flow_table(flows, plen, grid=1):
+    """Flows of equal packets (the last may be shorter) with the match finder taking every flow as ONE
+    stream whose look-ahead ends with each packet (lzs_b200_compress_flow_table_device on the emulator)."""
+    L = lib()
+    L.emu_set_seg.argtypes = [c_u32p]
+    src, pkt_off, pkt_len, _ = flows_layout(flows)
+    flow_off, flow_len, i = [], [], 0
+    for pk in flows:
+        flow_off.append(int(pkt_off[i]))
+        flow_len.append(sum(len(p) for p in pk))
+        i += len(pk)
+    flow_off, flow_len = np.array(flow_off, dtype=np.uint64), np.array(flow_len, dtype=np.uint32)
+    seg = np.full(len(flows), plen, dtype=np.uint32)
+    m = np.zeros(len(src) + 16, dtype=np.uint16)
+    L.emu_set_seg(_ptr(seg, c_u32p))
+    try:
+        L.emu_match(_ptr(src), _ptr(flow_off, c_u64p), _ptr(flow_len, c_u32p), _ptr(m, c_u16p), len(flows), grid)
+    finally:
+        L.emu_set_seg(None)
+    n = len(pkt_len)
+    caps = [int(l) + (int(l) + 7) // 8 + 3 for l in pkt_len]
+    dst, out_off, out_cap = _out_layout(caps, 0)
+    out_len = np.zeros(n, dtype=np.uint32)
+    L.emu_parse_pack(_ptr(src), _ptr(pkt_off, c_u64p), _ptr(pkt_len, c_u32p), _ptr(m, c_u16p), _ptr(dst),
+                     _ptr(out_off, c_u64p), _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), n)
+    flat = _collect(dst, out_off, caps, out_len, "packer")
+    res, i = [], 0
+    for pk in flows:
+        res.append(flat[i:i + len(pk)])
+        i += len(pk)
+    return res

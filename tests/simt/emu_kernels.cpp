@@ -36,6 +36,8 @@ extern "C" int emu_decode(const uint8_t *in, const uint64_t *in_off, const uint3
 
 static const uint32_t *g_emu_hist = nullptr;   /* kept-history lengths for the next emu_match / emu_decode (test knob) */
 extern "C" void emu_set_hist(const uint32_t *hist) { g_emu_hist = hist; }
+static const uint32_t *g_emu_seg = nullptr;    /* packet length per stream for the next emu_match (flows as one stream) */
+extern "C" void emu_set_seg(const uint32_t *seg) { g_emu_seg = seg; }
 
 extern "C" int emu_decode_hist(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                                const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
@@ -52,10 +54,10 @@ extern "C" int emu_match(const uint8_t *in, const uint64_t *in_off, const uint32
      * fast one recorded an exchange order it does not handle).  Returns that record. */
     uint32_t ctl[4] = {0, 0, 0, 0};
     simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
-        lzs::k1_match<false>(in, in_off, in_len, matches, n, ctl, g_emu_hist);
+        lzs::k1_match<false>(in, in_off, in_len, matches, n, ctl, g_emu_hist, g_emu_seg);
     });
     simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
-        lzs::k1_match<true>(in, in_off, in_len, matches, n, ctl, g_emu_hist);
+        lzs::k1_match<true>(in, in_off, in_len, matches, n, ctl, g_emu_hist, g_emu_seg);
     });
     return static_cast<int>(ctl[2]);
 }

@@ -376,6 +376,32 @@ def test_gpu_bulk_path_for_flows_with_kept_history():
             s = f * 4 + k
             assert comp[s * tab.cap:s * tab.cap + int(clen[s])].tobytes() == want[f][k], (f, k)
     with_hist = int(tab.comp_len.sum())
+    per_packet = (tab.comp.clone(), tab.comp_len.clone())
+    tab.compress_table()                               # every flow as one stream: the same bytes
+    torch.cuda.synchronize()
+    assert torch.equal(tab.comp_len, per_packet[1])
+    live = torch.arange(tab.cap, device=tab.comp.device)[None, :] < tab.comp_len[:, None]
+    assert not ((tab.comp[:tab.n * tab.cap].view(tab.n, tab.cap) != per_packet[0][:tab.n * tab.cap].view(tab.n, tab.cap)) & live).any()
     tab.compress(with_history=False)
     torch.cuda.synchronize()
     assert with_hist < int(tab.comp_len.sum()), "kept history should make later packets smaller"
+
+
+def test_emulated_flow_table_as_one_stream_per_flow():
+    """lzs_b200_compress_flow_table_device on the emulator: flows of equal packets, every flow ONE stream
+    for the match finder (look-ahead ending with each packet), equal to the reference's one state per flow."""
+    rng = np.random.default_rng(21)
+    vocab = helpers.corpus(helpers.CORPUS_TEXT, 1, 9000, seed=0x5EED0000 + 12).tobytes()
+    recs = helpers.corpus(helpers.CORPUS_BINARY, 1, 9000, seed=0x5EED0000 + 13).tobytes()
+    plen = 700
+    flows = []
+    for f in range(6):
+        base = vocab if f % 2 else recs
+        a = int(rng.integers(0, 3000))
+        total = int(rng.integers(plen + 1, 5 * plen))
+        data = base[a:a + total]
+        flows.append([data[k:k + plen] for k in range(0, len(data), plen)])
+    flows.append([b"q" * plen, b"q" * plen, b"q" * 13])                    # a run across packet borders
+    want = _reference_flows(flows)
+    assert emu.compress_flow_table(flows, plen) == want
+    assert emu.compress_flows(flows) == want                                  # and the per-packet form agrees
