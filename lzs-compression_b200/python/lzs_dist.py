@@ -59,6 +59,56 @@ def pack_streams(buf, off, length, align=ALIGN):
     return packed, dst_off
 
 
+def gather_compressed(buf, off, length, group=None, align=ALIGN, max_pad=1.25):
+    """Pack this rank's streams and all-gather-v them in one go.  Returns (payload, lengths of all
+    streams in rank order, byte offset of every stream in the payload, info dict).
+
+    When the ranks' byte counts are close (they are for shards of one corpus) the payload is laid out
+    with ONE stride per rank -- the largest rank's byte count, rounded up -- and every rank packs its
+    streams straight into its own part of the gathered buffer; the exchange is then a single in-place
+    NCCL all-gather, which on an NVSwitch box goes out once per rank (multicast) instead of once per
+    peer.  The parts' tails are padding; the returned offsets account for it.  Uneven ranks (stride more
+    than max_pad times the mean) fall back to pack_streams + all_gather_streams (exact sizes, grouped
+    send/recv)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = buf.device
+    length64 = length.to(torch.int64)
+    local_off, local_bytes = packed_layout(length64, align)
+    counts = torch.tensor([length.numel(), local_bytes], dtype=torch.int64, device=dev)
+    all_counts = torch.zeros(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = all_counts.view(world, 2).cpu()
+    n_of = [int(x) for x in all_counts[:, 0]]
+    b_of = [int(x) for x in all_counts[:, 1]]
+    stride = (max(b_of) + 255) // 256 * 256
+    uniform_n = len(set(n_of)) == 1
+    if not buf.is_cuda or not uniform_n or stride * world > max_pad * max(1, sum(b_of)):
+        packed, _ = pack_streams(buf, off, length, align)
+        payload, lens, offsets = all_gather_streams(packed, length, group, align)
+        return payload, lens, offsets, {"mode": "exact sizes, grouped send/recv", "payload_bytes": int(payload.numel())}
+    import lzs_b200 as B
+    payload = torch.empty(world * stride, dtype=torch.uint8, device=dev)
+    mine = payload[rank * stride:(rank + 1) * stride]
+    n = int(length.numel())
+    if n:
+        src_off = off.to(torch.int64).contiguous()
+        len32 = length.to(torch.int32).contiguous()
+        B.check(B.lib().lzs_b200_pack_streams_device(
+            buf.data_ptr(), src_off.data_ptr(), len32.data_ptr(), mine.data_ptr(), local_off.data_ptr(), n,
+            torch.cuda.current_stream(dev).cuda_stream))
+    dist.all_gather_into_tensor(payload, mine, group=group)              # in place: my part is already where it belongs
+    lens = torch.empty(world * n, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens, length64.contiguous(), group=group)
+    offsets = torch.empty_like(lens)
+    for r in range(world):
+        part = lens[r * n:(r + 1) * n]
+        off_r, _ = packed_layout(part, align)
+        offsets[r * n:(r + 1) * n] = off_r + r * stride
+    return payload, lens, offsets, {"mode": "one stride per rank, in-place all-gather", "payload_bytes": sum(b_of),
+                                    "stride": stride}
+
+
 def all_gather_streams(packed, lengths, group=None, align=ALIGN):
     """All-gather-v of packed payloads (as made by pack_streams with the same `align`).
     Returns (payload of all ranks in rank order, lengths of all streams in rank order,
