@@ -47,6 +47,9 @@ def _worker(rank, world, port, out_path):
     packed, packed_off = lzs_dist.pack_streams(torch.from_numpy(comp), off, torch.from_numpy(lens))
     assert packed.numel() % 16 == 0 and all(int(x) % 16 == 0 for x in packed_off)
     payload, all_len, all_off = lzs_dist.all_gather_streams(packed, torch.from_numpy(lens))
+    # the one-call form (packs and gathers; on CPU tensors it takes the exact-size path) must agree
+    p2, l2, o2, info = lzs_dist.gather_compressed(torch.from_numpy(comp), off, torch.from_numpy(lens))
+    assert torch.equal(p2, payload) and torch.equal(l2, all_len) and torch.equal(o2, all_off) and "exact" in info["mode"]
     torch.save({"payload": payload, "len": all_len, "off": all_off, "range": (lo, hi)}, out_path % rank)
     dist.barrier()
     dist.destroy_process_group()
