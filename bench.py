@@ -294,6 +294,18 @@ def run_gpu_arm(args):
         own_off = int(db.comp_off[n_chunks // 2])
         ln = int(db.comp_len[n_chunks // 2])
         assert torch.equal(payload[probe:probe + ln], db.comp[own_off:own_off + ln]), "gathered stream differs"
+        # ... and every rank must hold the SAME bytes for every stream: a checksum over all streams' words
+        # (position weighted) has to come out equal on all ranks
+        words = ((lens + 15) // 16 * 2)                                   # 8-byte words per stream, padding included
+        first = offs // 8
+        idx = torch.repeat_interleave(first, words) + (torch.arange(int(words.sum()), device=dev) -
+                                                       torch.repeat_interleave(torch.cumsum(words, 0) - words, words))
+        w64 = payload[:payload.numel() // 8 * 8].view(torch.int64)
+        chk = (w64[idx] * (torch.arange(idx.numel(), device=dev) % 1021 + 1)).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert int(lo) == int(hi), "the ranks gathered different bytes"
         own_bytes = int(((db.comp_len.to(torch.int64) + 15) // 16 * 16).sum().item())
         recv = int(ginfo["payload_bytes"]) - own_bytes
         gather = {"ms": best[0], "mode": ginfo["mode"],

@@ -118,6 +118,19 @@ int lzs_b200_compress_flow_table_device(const uint8_t *in, const uint64_t *flow_
 int lzs_b200_pack_streams_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint8_t *dst,
                                  const uint64_t *dst_off, uint32_t n_streams, void *stream);
 
+/* The pack kernel FUSED with the all-gather of the packed streams over NVLink peer memory (multi-GPU
+ * gather of variable-size outputs).  dst_ptrs: device array of n_dst addresses,
+ * one per rank of the box, of the SAME symmetric buffer as this GPU sees each rank's copy (peer
+ * mappings, e.g. torch.distributed._symmetric_memory: buffer_ptrs_dev); every stream is read once and
+ * stored at base + dst_off[s] in every copy.  The multicast form stores once per 16 bytes to the
+ * buffer's NVSwitch multicast address (multimem.st) and lets the switch replicate.  The caller
+ * separates the calls from the readers with a cross-rank barrier. */
+int lzs_b200_pack_streams_peers_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len,
+                                       uint8_t *const *dst_ptrs, uint32_t n_dst, uint64_t base, const uint64_t *dst_off,
+                                       uint32_t n_streams, void *stream);
+int lzs_b200_pack_streams_multicast_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint8_t *mc_ptr,
+                                           uint64_t base, const uint64_t *dst_off, uint32_t n_streams, void *stream);
+
 /* Individual stages of the compressor, for tests and profiling:
  * K1 writes one record per input byte, (len << 11) | offset with len 0 or 2..12;
  * K2+K3 turn records + input into streams.  `counter` is device scratch of at least 16 bytes

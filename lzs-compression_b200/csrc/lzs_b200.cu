@@ -137,6 +137,53 @@ __global__ void gather_streams_kernel(const uint8_t *__restrict__ src, const uin
     for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) to[i] = from[i];
 }
 
+/* The pack kernel fused with the all-gather of the packed streams: every stream is read once from
+ * this GPU's slots and written into the gathered buffer of EVERY rank of the box -- the buffers are
+ * one symmetric allocation, dst[r] the address of rank r's copy as THIS GPU sees it over NVLink
+ * (peer memory) -- at this rank's place in it (base) plus the stream's packed offset.  No staging
+ * copy and no separate collective: the NVLink transfer is the store. */
+__global__ void scatter_streams_peers_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                                             const uint32_t *__restrict__ len, uint8_t *const *__restrict__ dst,
+                                             uint32_t n_dst, uint64_t base, const uint64_t *__restrict__ dst_off, uint32_t n)
+{
+    const uint32_t s = blockIdx.x;
+    if (s >= n) return;
+    const uint4   *from = reinterpret_cast<const uint4 *>(src + src_off[s]);
+    const uint64_t at = base + dst_off[s];
+    const uint32_t vecs = (len[s] + 15u) >> 4;
+    /* every block starts with a different rank's copy, so that the GPUs of the box do not all store
+     * into the same GPU at the same moment */
+    const uint32_t d0 = (s + static_cast<uint32_t>(base >> 8)) % n_dst;
+    for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) {
+        const uint4 v = from[i];
+        for (uint32_t k = 0; k < n_dst; k++) {
+            const uint32_t d = d0 + k < n_dst ? d0 + k : d0 + k - n_dst;
+            reinterpret_cast<uint4 *>(dst[d] + at)[i] = v;
+        }
+    }
+}
+
+/* The same through the NVSwitch multicast address of the symmetric buffer: ONE store per 16 bytes,
+ * replicated to all ranks inside the switch (multimem.st), so the sending GPU's NVLink carries every
+ * byte once instead of once per peer. */
+__global__ void scatter_streams_multicast_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
+                                                 const uint32_t *__restrict__ len, uint8_t *__restrict__ mc, uint64_t base,
+                                                 const uint64_t *__restrict__ dst_off, uint32_t n)
+{
+    const uint32_t s = blockIdx.x;
+    if (s >= n) return;
+    const uint4   *from = reinterpret_cast<const uint4 *>(src + src_off[s]);
+    uint8_t       *to = mc + base + dst_off[s];
+    const uint32_t vecs = (len[s] + 15u) >> 4;
+    for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x) {
+        const uint4 v = from[i];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(to + 16ull * i),
+                     "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                     "f"(__uint_as_float(v.w))
+                     : "memory");
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -426,6 +473,31 @@ int lzs_b200_pack_streams_device(const uint8_t *src, const uint64_t *src_off, co
     if (!src || !src_off || !len || !dst || !dst_off) return fail(LZS_B200_EINVAL, "null pointer");
     gather_streams_kernel<<<n_streams, 128, 0, static_cast<cudaStream_t>(stream)>>>(src, src_off, len, dst, dst_off,
                                                                                     n_streams);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+int lzs_b200_pack_streams_peers_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len,
+                                       uint8_t *const *dst_ptrs, uint32_t n_dst, uint64_t base, const uint64_t *dst_off,
+                                       uint32_t n_streams, void *stream)
+{
+    if (n_streams == 0 || n_dst == 0) return LZS_B200_OK;
+    if (!src || !src_off || !len || !dst_ptrs || !dst_off) return fail(LZS_B200_EINVAL, "null pointer");
+    scatter_streams_peers_kernel<<<n_streams, 128, 0, static_cast<cudaStream_t>(stream)>>>(src, src_off, len, dst_ptrs, n_dst,
+                                                                                          base, dst_off, n_streams);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+int lzs_b200_pack_streams_multicast_device(const uint8_t *src, const uint64_t *src_off, const uint32_t *len, uint8_t *mc_ptr,
+                                           uint64_t base, const uint64_t *dst_off, uint32_t n_streams, void *stream)
+{
+    if (n_streams == 0) return LZS_B200_OK;
+    if (!src || !src_off || !len || !mc_ptr || !dst_off) return fail(LZS_B200_EINVAL, "null pointer");
+    scatter_streams_multicast_kernel<<<n_streams, 128, 0, static_cast<cudaStream_t>(stream)>>>(src, src_off, len, mc_ptr, base,
+                                                                                              dst_off, n_streams);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return LZS_B200_OK;

@@ -84,6 +84,8 @@ def lib():
                                               ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp]
     L.lzs_b200_set_decode_lanes.argtypes = [ctypes.c_int]
     L.lzs_b200_pack_streams_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
+    L.lzs_b200_pack_streams_peers_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
+    L.lzs_b200_pack_streams_multicast_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
     L.lzs_b200_release.restype = ctypes.c_int
     L.lzs_b200_chunk_count.restype = ctypes.c_uint32
     L.lzs_b200_chunk_count.argtypes = [ctypes.c_uint64, ctypes.c_uint32]

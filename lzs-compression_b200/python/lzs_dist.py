@@ -88,9 +88,19 @@ def gather_compressed(buf, off, length, group=None, align=ALIGN, max_pad=1.25):
         payload, lens, offsets = all_gather_streams(packed, length, group, align)
         return payload, lens, offsets, {"mode": "exact sizes, grouped send/recv", "payload_bytes": int(payload.numel())}
     import lzs_b200 as B
+    n = int(length.numel())
+    fused = _symmetric_gather(B, buf, off, length, local_off, n, world, rank, stride, group)
+    if fused is not None:
+        payload, mode = fused
+        lens = torch.empty(world * n, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(lens, length64.contiguous(), group=group)
+        offsets = torch.empty_like(lens)
+        for r in range(world):
+            off_r, _ = packed_layout(lens[r * n:(r + 1) * n], align)
+            offsets[r * n:(r + 1) * n] = off_r + r * stride
+        return payload, lens, offsets, {"mode": mode, "payload_bytes": sum(b_of), "stride": stride}
     payload = torch.empty(world * stride, dtype=torch.uint8, device=dev)
     mine = payload[rank * stride:(rank + 1) * stride]
-    n = int(length.numel())
     if n:
         src_off = off.to(torch.int64).contiguous()
         len32 = length.to(torch.int32).contiguous()
@@ -107,6 +117,69 @@ def gather_compressed(buf, off, length, group=None, align=ALIGN, max_pad=1.25):
         offsets[r * n:(r + 1) * n] = off_r + r * stride
     return payload, lens, offsets, {"mode": "one stride per rank, in-place all-gather", "payload_bytes": sum(b_of),
                                     "stride": stride}
+
+
+_symm = {}          # (device, group) -> (capacity, symmetric buffer, handle)
+
+
+def _symmetric_gather(B, buf, off, length, local_off, n, world, rank, stride, group):
+    """The pack kernel FUSED with the all-gather: the gathered payload lives in a symmetric buffer (one
+    allocation per rank, every rank's copy mapped into every GPU over NVLink:
+    torch.distributed._symmetric_memory), and this rank's pack kernel stores each of its streams straight
+    into all copies -- through the NVSwitch multicast address when the box has one (one store, replicated
+    in the switch), else with one store per peer.  Cross-rank barriers before (the previous contents may
+    still be read) and after (all stores have landed).  LZS_B200_GATHER = nccl | peers | multicast picks a
+    path; default: the fused kernel with one store per peer up to 4 ranks, NCCL's in-place all-gather
+    above (what measured fastest).  Returns (payload tensor, mode) or None (the caller uses NCCL)."""
+    import os
+    want = os.environ.get("LZS_B200_GATHER", "auto")
+    if want == "auto":
+        # measured on B200 / NVSwitch (profiles/README.md): 2 ranks: 1.7 ms fused against 2.2 ms NCCL;
+        # 8 ranks: 9.8 ms fused (10.6 with multicast stores) against 9.2 ms for NCCL's in-place all-gather
+        want = "peers" if world <= 4 else "nccl"
+    if want == "nccl":
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = buf.device
+        key = (dev.index, id(group))
+        need = world * stride
+        ent = _symm.get(key)
+        if ent is None or ent[0] < need:
+            cap = (need + (need >> 3) + (1 << 26)) >> 26 << 26          # some head room, 64 MiB granules
+            # every rank must agree on the size of a symmetric allocation
+            cap_t = torch.tensor([cap], dtype=torch.int64, device=dev)
+            dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
+            cap = int(cap_t.item())
+            sbuf = symm_mem.empty(cap, dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(sbuf, group if group is not None else dist.group.WORLD)
+            ent = (cap, sbuf, hdl)
+            _symm[key] = ent
+        cap, sbuf, hdl = ent
+        mc = int(hdl.multicast_ptr or 0)                                 # 0: no NVSwitch multicast object for this buffer
+        mode = "multicast" if (mc and want == "multicast") else "peers"
+        if want == "multicast" and not mc:
+            return None
+        src_off = off.to(torch.int64).contiguous()
+        len32 = length.to(torch.int32).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        hdl.barrier(channel=0)                                           # nobody still reads the previous payload
+        if n:
+            if mode == "multicast":
+                B.check(B.lib().lzs_b200_pack_streams_multicast_device(
+                    buf.data_ptr(), src_off.data_ptr(), len32.data_ptr(), mc, rank * stride, local_off.data_ptr(), n, stream))
+            else:
+                B.check(B.lib().lzs_b200_pack_streams_peers_device(
+                    buf.data_ptr(), src_off.data_ptr(), len32.data_ptr(), int(hdl.buffer_ptrs_dev), world, rank * stride,
+                    local_off.data_ptr(), n, stream))
+        hdl.barrier(channel=1)                                           # every rank's stores have landed everywhere
+        return sbuf[:need], ("pack fused with the all-gather over NVLink peer memory, "
+                             + ("NVSwitch multicast stores" if mode == "multicast" else "one store per peer"))
+    except Exception as e:                                               # no symmetric memory on this box / torch
+        if want in ("peers", "multicast"):
+            raise
+        _symm["error"] = repr(e)
+        return None
 
 
 def all_gather_streams(packed, lengths, group=None, align=ALIGN):
