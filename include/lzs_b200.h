@@ -243,6 +243,19 @@ int lzs_b200_set_zero_copy_output(int on);
  * assumes).  Same records, several times slower. */
 int lzs_b200_set_force_safe_match(int on);
 
+/* Long streams.  The parse of an LZS stream is serial (lzs-compression.c:301-447: where a token
+ * starts depends on where the one before ended), and one warp per stream leaves the GPU empty when a
+ * batch has few streams -- one lzs_compress call on a large buffer has one.  A batch of at most 2048
+ * streams that average two pieces or more (in_span >= 2 * piece * n_streams) is therefore cut: every
+ * stream into pieces of `piece` bytes, matches found and pieces parsed in parallel, the pieces'
+ * tokens stitched into the one stream the reference produces, byte for byte (csrc/k23_pieces.cuh).
+ * Default 65536 (environment: LZS_B200_PIECE); 0 turns the cutting off, 64 .. 2^28 sets the piece
+ * size.  lzs_b200_compress_scratch_bytes() includes the piece table for the setting in force when it
+ * is called; with less scratch than that the streams are not cut.  Streams of a batch that is cut
+ * must not overlap in `in`.  Applies to lzs_b200_compress_batch_device, the host batch calls and
+ * lzs_compress / lzs_simple_compress; the decoder has no counterpart. */
+int lzs_b200_set_piece_bytes(uint32_t bytes);
+
 /* Number of kernels launched by this library in the calling process so far. */
 uint64_t lzs_b200_kernel_launches(void);
 

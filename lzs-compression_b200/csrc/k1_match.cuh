@@ -157,6 +157,7 @@ struct K1Tile {
     uint32_t sid, t0, tile_n, n, v0;
     uint32_t skip;      /* the first `skip` positions are kept history of the flow (built into the tables, not matched) */
     uint32_t seg;       /* 0, or the stream is a flow of packets of this many bytes: tokens end with the packet */
+    uint32_t look;      /* the last `look` positions belong to the NEXT piece of a long stream: built and compared against, not matched */
 };
 
 /* Hash of the k-gram that starts the 12 bytes (w0, w1, w2); (m0, m1, m2) mask the bytes that
@@ -750,7 +751,7 @@ __device__ __forceinline__ void k1_query_chunks(const K1Tile &d, uint32_t *next_
             /* a flow of equal packets as ONE stream: the look-ahead ends with the packet position i lies in
              * (what the reference does when a packet is flushed with add_end_marker), the history does not */
             const uint32_t n_eff = d.seg ? umin32(d.n, (i / d.seg + 1u) * d.seg) : d.n;
-            if (i >= d.skip) mout[i - d.skip] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, n_eff));
+            if (i >= d.skip && i < d.n - d.look) mout[i - d.skip] = static_cast<match_t>(k1_query(links, runs, W, d.v0, i, n_eff));
         }
         __syncwarp();
     }
@@ -763,7 +764,8 @@ template <bool kSafe>
 __global__ void __launch_bounds__(kK1Threads, 1)
 k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
          const uint32_t *__restrict__ in_len, match_t *__restrict__ matches, uint32_t n_streams,
-         uint32_t *__restrict__ ctl, const uint32_t *__restrict__ hist_len, const uint32_t *__restrict__ seg_len)
+         uint32_t *__restrict__ ctl, const uint32_t *__restrict__ hist_len, const uint32_t *__restrict__ seg_len,
+         const uint32_t *__restrict__ look_len = nullptr)
 {
     if (kSafe && *reinterpret_cast<volatile uint32_t *>(ctl + 2) == 0u) return;
     uint32_t *next_stream = ctl + (kSafe ? 1 : 0);
@@ -825,7 +827,12 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
              * look-ahead ends with the packet). */
             const uint32_t own = in_len[sid];
             const uint32_t hist = (hist_len != nullptr && own != 0u) ? umin32(hist_len[sid], kWindow) : 0u;
-            const uint32_t n = own + hist;
+            /* Pieces of a long stream (k23_pieces.cuh): the piece is followed in memory by the rest of its
+             * stream, and its last positions may match up to 11 bytes into it -- the `look` bytes behind the
+             * piece are part of what the tables and the compares see, and their own positions are left
+             * to the next piece. */
+            const uint32_t look = (look_len != nullptr && own != 0u) ? umin32(look_len[sid], kSearchMax - 1u) : 0u;
+            const uint32_t n = own + hist + look;
             const uint8_t *src = in + in_off[sid] - hist;
             /* last aligned word that holds a byte of the stream (n > 0 inside the tile loop) */
             const uintptr_t wlast = (reinterpret_cast<uintptr_t>(src) + (n ? n - 1u : 0u)) & ~static_cast<uintptr_t>(3);
@@ -882,6 +889,7 @@ k1_match(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     K1Tile d;
                     d.sid = sid; d.t0 = t0; d.tile_n = umin32(kK1Tile, n - t0); d.n = n; d.v0 = v0; d.skip = hist;
                     d.seg = seg_len != nullptr ? seg_len[sid] : 0u;
+                    d.look = look;
                     s_desc[g & 7u] = d;
                     s_qnext[g & 15u] = 0;    /* nobody can still be on tile g - 16 */
                 }

@@ -22,6 +22,7 @@
 #include "corpus.h"
 #include "k1_match.cuh"
 #include "k23_parse_pack.cuh"
+#include "k23_pieces.cuh"
 #include "k4_decode.cuh"
 
 namespace {
@@ -31,6 +32,7 @@ std::atomic<uint64_t>      g_launches{0};
 std::atomic<int>           g_decode_lanes{0};
 std::atomic<int>           g_force_safe_match{0};
 std::atomic<int>           g_zero_copy_out{-1};   /* -1: read LZS_B200_ZEROCOPY on first use */
+std::atomic<int64_t>       g_piece_bytes{-1};     /* -1: read LZS_B200_PIECE on first use; 0: long streams are never cut */
 
 int fail(int code, const char *fmt, ...)
 {
@@ -116,6 +118,45 @@ bool order_streams()
 }
 
 constexpr size_t kCounterBytes = 256;    /* work counters live at the start of scratch */
+
+/* Long streams are cut into pieces of this many bytes for the match finder and the parse/pack
+ * kernels (k23_pieces.cuh) when the streams of a batch average two pieces or more -- fewer streams
+ * than that do not fill the GPU with one warp each.  LZS_B200_PIECE sets it (0: never cut). */
+uint32_t piece_bytes()
+{
+    int64_t v = g_piece_bytes.load();
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_PIECE");
+        v = e ? atoll(e) : 65536;
+        if (v < 0 || v > (1ll << 28)) v = 65536;
+        if (v != 0 && v < 64) v = 64;
+        g_piece_bytes.store(v);
+    }
+    return static_cast<uint32_t>(v);
+}
+/* entries of the piece table for a batch over in_span bytes: in_span / P pieces, one more per
+ * stream, and a batch is only cut when it has at most in_span / 2P streams */
+uint32_t piece_table_entries(uint64_t in_span, uint32_t piece)
+{
+    const uint64_t e = in_span / piece + in_span / (2ull * piece) + 16u;
+    return e > 0x7FFFFFFFull ? 0x7FFFFFFFu : static_cast<uint32_t>(e);
+}
+size_t matches_bytes(uint64_t in_span) { return align_up(static_cast<size_t>(in_span) * sizeof(lzs::match_t) + 64, 256); }
+/* Cut the streams of this batch?  Decided from what the host knows without looking at the lengths:
+ * few streams (one warp per stream fills the parse kernel from ~2000 streams on: measured, 1 GiB in
+ * 512 KiB chunks is where cut and uncut meet, profiles/r2_pieces_bench.jsonl) that average two
+ * pieces or more, and scratch with room for the piece table.  A batch of many short streams with a
+ * long one among them is not cut.  Returns the table's entries, 0 = do not cut. */
+constexpr uint32_t kCutStreamsMax = 2048;
+uint32_t cut_into_pieces(uint32_t n_streams, uint64_t in_span, size_t scratch_bytes, uint32_t *piece_out)
+{
+    const uint32_t piece = piece_bytes();
+    if (piece == 0 || n_streams > kCutStreamsMax || static_cast<uint64_t>(n_streams) * 2u * piece > in_span) return 0;
+    const uint32_t cap = piece_table_entries(in_span, piece);
+    if (scratch_bytes < kCounterBytes + matches_bytes(in_span) + lzs::piece_table_bytes(cap)) return 0;
+    *piece_out = piece;
+    return cap;
+}
 
 __global__ void corpus_fill_kernel(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
                                    uint64_t n, uint64_t seed, int kind)
@@ -246,7 +287,16 @@ int lzs_b200_set_force_safe_match(int on)
 
 size_t lzs_b200_compress_scratch_bytes(uint64_t in_span)
 {
-    return kCounterBytes + align_up(static_cast<size_t>(in_span) * sizeof(lzs::match_t) + 64, 256);
+    const uint32_t piece = piece_bytes();
+    const size_t   table = piece ? align_up(lzs::piece_table_bytes(piece_table_entries(in_span, piece)), 256) : 0;
+    return kCounterBytes + matches_bytes(in_span) + table;
+}
+
+int lzs_b200_set_piece_bytes(uint32_t bytes)
+{
+    if (bytes != 0 && (bytes < 64 || bytes > (1u << 28))) return fail(LZS_B200_EINVAL, "piece size must be 0 or 64 .. 2^28");
+    g_piece_bytes.store(bytes);
+    return LZS_B200_OK;
 }
 
 size_t lzs_b200_decompress_scratch_bytes(void) { return kCounterBytes; }
@@ -261,7 +311,8 @@ size_t lzs_b200_decompress_scratch_bytes_for(uint32_t n_streams)
 
 namespace {
 int match_batch(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, const uint32_t *hist_len,
-                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream, const uint32_t *seg_len = nullptr)
+                uint16_t *matches, uint32_t n_streams, uint32_t *counter, void *stream, const uint32_t *seg_len = nullptr,
+                const uint32_t *look_len = nullptr)
 {
     if (n_streams == 0) return LZS_B200_OK;
     if (!in || !in_off || !in_len || !matches || !counter) return fail(LZS_B200_EINVAL, "null pointer");
@@ -275,12 +326,40 @@ int match_batch(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_le
     if (g_force_safe_match.load()) CUDA_TRY(cudaMemsetAsync(counter + 2, 1, 1, st));
     const unsigned grid = n_streams < static_cast<uint32_t>(d->sms) ? n_streams : static_cast<unsigned>(d->sms);
     lzs::k1_match<false><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
-                                                                          counter, hist_len, seg_len);
+                                                                          counter, hist_len, seg_len, look_len);
     /* the exact-for-any-hardware variant: returns at once unless the fast launch saw an exchange
      * order it does not handle (never on sm_100a); on the stream, so nothing waits on the host */
     lzs::k1_match<true><<<grid, lzs::kK1Threads, lzs::kK1SmemBytes, st>>>(in, in_off, in_len, matches, n_streams,
-                                                                         counter, hist_len, seg_len);
+                                                                         counter, hist_len, seg_len, look_len);
     g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+/* The compressor for few long streams: plan, K1 over the pieces, then the four passes of
+ * k23_pieces.cuh.  All on the stream; nothing comes back to the host. */
+int compress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                    const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams,
+                    uint32_t piece, uint32_t cap, uint32_t *counter, uint16_t *matches, void *table_mem, void *stream)
+{
+    if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len) return fail(LZS_B200_EINVAL, "null pointer");
+    cudaStream_t          st = static_cast<cudaStream_t>(stream);
+    const lzs::PieceTable t = lzs::piece_table_at(table_mem, cap);
+    CUDA_TRY(cudaMemsetAsync(t.count, 0, 256, st));
+    CUDA_TRY(cudaMemsetAsync(t.len, 0, static_cast<size_t>(cap) * sizeof(uint32_t), st));
+    lzs::k23p_plan_count<<<1, lzs::kPlanThreads, 0, st>>>(in_len, n_streams, piece, t);
+    lzs::k23p_plan_fill<<<n_streams, 128, 0, st>>>(in_off, in_len, out_len, n_streams, piece, t);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    int rc = match_batch(in, t.off, t.len, t.hist, matches, cap, counter, stream, nullptr, t.look);
+    if (rc) return rc;
+    const unsigned pgrid = (cap + lzs::kPieceWarps - 1) / lzs::kPieceWarps;
+    const unsigned sgrid = (n_streams + lzs::kPieceWarps - 1) / lzs::kPieceWarps;
+    lzs::k23p_spec<<<pgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, piece, t);
+    lzs::k23p_fix<<<pgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, piece, t);
+    lzs::k23p_sweep<<<sgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, out_cap, out_len, n_streams, t);
+    lzs::k23p_pack<<<pgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, out, out_off, out_cap, t);
+    g_launches += 4;
     CUDA_TRY(cudaGetLastError());
     return LZS_B200_OK;
 }
@@ -308,7 +387,7 @@ int lzs_b200_compress_flow_table_device(const uint8_t *in, const uint64_t *flow_
 {
     if (n_flows == 0 || n_packets == 0) return LZS_B200_OK;
     if (!seg_len) return fail(LZS_B200_EINVAL, "null pointer");
-    if (!scratch || scratch_bytes < lzs_b200_compress_scratch_bytes(in_span))
+    if (!scratch || scratch_bytes < kCounterBytes + matches_bytes(in_span))
         return fail(LZS_B200_EINVAL, "scratch too small: need %zu bytes, got %zu",
                     lzs_b200_compress_scratch_bytes(in_span), scratch_bytes);
     uint32_t *counter = static_cast<uint32_t *>(scratch);
@@ -329,7 +408,7 @@ int lzs_b200_compress_flows_batch_device(const uint8_t *in, const uint64_t *in_o
                                          uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream)
 {
     if (n_streams == 0) return LZS_B200_OK;
-    if (!scratch || scratch_bytes < lzs_b200_compress_scratch_bytes(in_span))
+    if (!scratch || scratch_bytes < kCounterBytes + matches_bytes(in_span))
         return fail(LZS_B200_EINVAL, "scratch too small: need %zu bytes, got %zu",
                     lzs_b200_compress_scratch_bytes(in_span), scratch_bytes);
     uint32_t *counter = static_cast<uint32_t *>(scratch);
@@ -363,11 +442,18 @@ int lzs_b200_compress_batch_device(const uint8_t *in, const uint64_t *in_off, co
                                    void *scratch, size_t scratch_bytes, void *stream)
 {
     if (n_streams == 0) return LZS_B200_OK;
-    if (!scratch || scratch_bytes < lzs_b200_compress_scratch_bytes(in_span))
+    const size_t plain = kCounterBytes + matches_bytes(in_span);
+    if (!scratch || scratch_bytes < plain)
         return fail(LZS_B200_EINVAL, "scratch too small: need %zu bytes, got %zu",
                     lzs_b200_compress_scratch_bytes(in_span), scratch_bytes);
     uint32_t *counter = static_cast<uint32_t *>(scratch);
     uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(scratch) + kCounterBytes);
+    /* few long streams: cut into pieces (k23_pieces.cuh) */
+    uint32_t       piece = 0;
+    const uint32_t cap = cut_into_pieces(n_streams, in_span, scratch_bytes, &piece);
+    if (cap)
+        return compress_pieces(in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, piece, cap, counter,
+                               matches, static_cast<uint8_t *>(scratch) + plain, stream);
     int rc = lzs_b200_match_batch_device(in, in_off, in_len, matches, n_streams, counter, stream);
     if (rc) return rc;
     return lzs_b200_parse_pack_batch_device(in, in_off, in_len, matches, out, out_off, out_cap, out_len,
@@ -919,6 +1005,9 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
         for (auto &w : p.work) CUDA_TRY(cudaStreamWaitEvent(w, ev[nslice], 0));
         CUDA_TRY(cudaStreamWaitEvent(p.up, ev[nslice], 0));
         uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(p.buf[S_SCRATCH]) + kCounterBytes);
+        uint32_t       piece = 0;
+        const uint32_t piece_cap = decompress ? 0u : cut_into_pieces(n, in_span, p.cap[S_SCRATCH], &piece);
+        const bool     pieces = piece_cap != 0;
         /* LZS_B200_TRACE=1 prints when every stage of every slice finished (ms from the start) */
         const bool               trace = getenv("LZS_B200_TRACE") != nullptr;
         std::vector<cudaEvent_t> tr(trace ? nslice * 4 + 1 : 0);
@@ -942,6 +1031,12 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
             if (decompress) {
                 rc = lzs_b200_decompress_batch_device(d_in, d_inoff + a, d_inlen + a, d_out, d_outoff + a, d_outcap + a,
                                                       d_outlen + a, cnt, d_cnt + k * 512, 256, ws);
+            } else if (pieces) {
+                /* few long streams: cut into pieces; the slices share one piece table, which is safe
+                 * because the compressor's slices follow each other on one stream */
+                rc = compress_pieces(d_in, d_inoff + a, d_inlen + a, d_out, d_outoff + a, d_outcap + a, d_outlen + a, cnt,
+                                     piece, piece_cap, reinterpret_cast<uint32_t *>(d_cnt + k * 512), matches,
+                                     static_cast<uint8_t *>(p.buf[S_SCRATCH]) + kCounterBytes + matches_bytes(in_span), ws);
             } else {
                 rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
                                                  reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
@@ -1056,6 +1151,8 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
     uint32_t *d_outlen = static_cast<uint32_t *>(p.buf[S_OUTLEN]);
     uint64_t *d_packoff = static_cast<uint64_t *>(p.buf[S_PACKOFF]);
     uint16_t *matches = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(p.buf[S_SCRATCH]) + kCounterBytes);
+    uint32_t       piece = 0;
+    const uint32_t piece_cap = cut_into_pieces(n, in_span, p.cap[S_SCRATCH], &piece);
 
     CUDA_TRY(cudaMemcpyAsync(d_inoff, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_inlen, in_len, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -1082,15 +1179,22 @@ int run_compress_packed(const uint8_t *in, const uint64_t *in_off, const uint32_
         mark(k, 1, p.up);
         CUDA_TRY(cudaEventRecord(up_ev[k], p.up));
         CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
-        rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
-                                         reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
-        mark(k, 2, ws);
-        if (!rc && parse_side_streams() > 0) {
+        if (piece_cap) {                           /* few long streams: cut into pieces, as in run_host_batch */
+            rc = compress_pieces(d_in, d_inoff + a, d_inlen + a, d_slots, d_slotoff + a, d_slotcap + a, d_outlen + a, cnt,
+                                 piece, piece_cap, reinterpret_cast<uint32_t *>(d_cnt + k * 512), matches,
+                                 static_cast<uint8_t *>(p.buf[S_SCRATCH]) + kCounterBytes + matches_bytes(in_span), ws);
+            mark(k, 2, ws);
+        } else {
+            rc = lzs_b200_match_batch_device(d_in, d_inoff + a, d_inlen + a, matches, cnt,
+                                             reinterpret_cast<uint32_t *>(d_cnt + k * 512), ws);
+            mark(k, 2, ws);
+        }
+        if (!rc && !piece_cap && parse_side_streams() > 0) {
             CUDA_TRY(cudaEventRecord(up_ev[k], ws));                    /* reused: the upload has been waited for */
             ws = p.work[1 + k % static_cast<uint32_t>(parse_side_streams())];
             CUDA_TRY(cudaStreamWaitEvent(ws, up_ev[k], 0));
         }
-        if (!rc)
+        if (!rc && !piece_cap)
             rc = lzs_b200_parse_pack_batch_device(d_in, d_inoff + a, d_inlen + a, matches, d_slots, d_slotoff + a,
                                                   d_slotcap + a, d_outlen + a, cnt, ws);
         if (rc) break;

@@ -83,6 +83,7 @@ def lib():
     L.lzs_b200_corpus_fill_device.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
                                               ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp]
     L.lzs_b200_set_decode_lanes.argtypes = [ctypes.c_int]
+    L.lzs_b200_set_piece_bytes.argtypes = [ctypes.c_uint32]
     L.lzs_b200_pack_streams_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
     L.lzs_b200_pack_streams_peers_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
     L.lzs_b200_pack_streams_multicast_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
@@ -236,6 +237,11 @@ def decompress_streams_status(streams, caps, device="cuda:0"):
 
 
 # ---------------------------------------------------------------------- device batches
+
+def set_piece_bytes(n):
+    """Piece size for long streams (include/lzs_b200.h: lzs_b200_set_piece_bytes); 0 = never cut."""
+    check(lib().lzs_b200_set_piece_bytes(int(n)))
+
 
 class DeviceBatch:
     """Device-resident uniform chunking of one torch.uint8 buffer (plumbing only:

@@ -119,6 +119,28 @@ def compress(streams, caps=None, grid=1, align=16, lead=0, out_lead=0):
     return _collect(dst, out_off, caps, out_len, "packer")
 
 
+def compress_pieces(streams, piece, caps=None, grid=1, align=16, lead=0, out_lead=0, cap_entries=None):
+    """The compressor for long streams (csrc/k23_pieces.cuh): streams cut into pieces of `piece` bytes.
+    Returns (streams, stats) with stats = [pieces, left open by spec, by fix, pieces holding a token]."""
+    src, in_off, in_len = pack_streams(streams, align, lead)
+    if caps is None:
+        caps = [len(s) + (len(s) + 7) // 8 + 3 for s in streams]
+    dst, out_off, out_cap = _out_layout(caps, out_lead)
+    out_len = np.zeros(len(streams), dtype=np.uint32)
+    stats = np.zeros(4, dtype=np.uint32)
+    if cap_entries is None:
+        cap_entries = sum(max(1, -(-len(s) // piece)) for s in streams) + 3
+    L = lib()
+    L.emu_compress_pieces.argtypes = [c_u8p, c_u64p, c_u32p, ctypes.c_uint64, c_u8p, c_u64p, c_u32p, c_u32p,
+                                      ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint, c_u32p]
+    over = L.emu_compress_pieces(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), len(src), _ptr(dst),
+                                 _ptr(out_off, c_u64p), _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams),
+                                 piece, cap_entries, grid, _ptr(stats, c_u32p))
+    if over:
+        return None, stats
+    return _collect(dst, out_off, caps, out_len, "packer"), stats
+
+
 # ---- flows with kept history (lzs_b200_*_flows_batch_device on the emulator) ----
 
 def flows_layout(flows, lead=0):

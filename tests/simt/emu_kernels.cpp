@@ -5,8 +5,10 @@
  * has no GPU; the shipped library never contains or calls any of this.
  */
 #define LZS_SIMT_EMU 1
+#include <vector>
 #include "../../lzs-compression_b200/csrc/k1_match.cuh"
 #include "../../lzs-compression_b200/csrc/k23_parse_pack.cuh"
+#include "../../lzs-compression_b200/csrc/k23_pieces.cuh"
 #include "../../lzs-compression_b200/csrc/k4_decode.cuh"
 
 template <int G>
@@ -75,6 +77,47 @@ extern "C" int emu_parse_pack(const uint8_t *in, const uint64_t *in_off, const u
         lzs::k23_parse_pack(in, in_off, in_len, matches, out, out_off, out_cap, out_len, n);
     });
     return 0;
+}
+
+/* The compressor for long streams (k23_pieces.cuh), the launches of compress_pieces() in
+ * lzs_b200.cu one after the other.  `cap` entries of piece table; returns the table's overflow flag.
+ * stats (optional, 4 words): pieces, pieces left open by spec, by fix, pieces in use. */
+extern "C" int emu_compress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint64_t in_span,
+                                   uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                                   uint32_t n, uint32_t piece, uint32_t cap, unsigned grid, uint32_t *stats)
+{
+    std::vector<uint64_t> mem((lzs::piece_table_bytes(cap) + 7) / 8, 0);
+    std::vector<uint16_t> matches(in_span + 64, 0xFFFF);
+    const lzs::PieceTable t = lzs::piece_table_at(mem.data(), cap);
+    simt::launch(dim3(1), dim3(lzs::kPlanThreads), 0, [&] { lzs::k23p_plan_count(in_len, n, piece, t); });
+    simt::launch(dim3(n), dim3(128), 0, [&] { lzs::k23p_plan_fill(in_off, in_len, out_len, n, piece, t); });
+    uint32_t ctl[4] = {0, 0, 0, 0};
+    simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
+        lzs::k1_match<false>(in, t.off, t.len, matches.data(), cap, ctl, t.hist, nullptr, t.look);
+    });
+    simt::launch(dim3(grid), dim3(lzs::kK1Threads), lzs::kK1SmemBytes, [&] {
+        lzs::k1_match<true>(in, t.off, t.len, matches.data(), cap, ctl, t.hist, nullptr, t.look);
+    });
+    const unsigned pgrid = (cap + lzs::kPieceWarps - 1) / lzs::kPieceWarps;
+    const unsigned sgrid = (n + lzs::kPieceWarps - 1) / lzs::kPieceWarps;
+    simt::launch(dim3(pgrid), dim3(lzs::kPieceThreads), 0, [&] { lzs::k23p_spec(in, in_off, in_len, matches.data(), piece, t); });
+    simt::launch(dim3(pgrid), dim3(lzs::kPieceThreads), 0, [&] { lzs::k23p_fix(in, in_off, in_len, matches.data(), piece, t); });
+    simt::launch(dim3(sgrid), dim3(lzs::kPieceThreads), 0, [&] {
+        lzs::k23p_sweep(in, in_off, in_len, matches.data(), out_cap, out_len, n, t);
+    });
+    simt::launch(dim3(pgrid), dim3(lzs::kPieceThreads), 0, [&] {
+        lzs::k23p_pack(in, in_off, in_len, matches.data(), out, out_off, out_cap, t);
+    });
+    if (stats) {
+        stats[0] = t.count[0];
+        stats[1] = stats[2] = stats[3] = 0;
+        for (uint32_t i = 0; i < t.count[0]; i++) {
+            if (t.flags[i] & lzs::kPieceSpecOpen) stats[1]++;
+            if (t.flags[i] & lzs::kPieceFixOpen) stats[2]++;
+            if (t.entry[i] < t.p0[i] + t.len[i]) stats[3]++;
+        }
+    }
+    return static_cast<int>(t.count[1]);
 }
 
 #include "../../lzs-compression_b200/csrc/incremental.cuh"

@@ -513,3 +513,83 @@ def test_registered_torch_operators():
     assert [got[a:a + len(d)].tobytes() for a, d in zip(off, data)] == data
     assert out_len.cpu().tolist() == [len(d) for d in data]
     assert all(s in (0x04, 0x08) for s in status.cpu().tolist())      # end marker seen, or capacity reached exactly at it
+
+
+# ---------------------------------------------------------------- long streams cut into pieces
+
+def _reference_streams(data):
+    ref = helpers.reference() or helpers.oracle()
+    return [ref.compress(d) for d in data]
+
+
+def test_long_streams_small_pieces_all_streams_against_reference(B):
+    """csrc/k23_pieces.cuh with a piece size far below the stream size, so that 16 borders fall into
+    every stream of a 64 MiB batch of 64 KiB chunks: all 1024 streams byte for byte against the
+    unmodified reference, and the round trip.  The launch counter says the piece path really ran."""
+    import torch
+    total, chunk = 64 << 20, 65536
+    B.set_piece_bytes(4096)
+    try:
+        db = B.DeviceBatch(total, chunk)
+        db.fill(B.CORPUS_MIXED, 0x5EED0000 + 21)
+        before = B.lib().lzs_b200_kernel_launches()
+        db.compress()
+        assert B.lib().lzs_b200_kernel_launches() - before == 8      # plan x2, K1 x2, spec, fix, sweep, pack
+        db.decompress()
+        torch.cuda.synchronize()
+        assert db.roundtrip_ok()
+        assert _compare_all_streams(B, db, "pieces of 4 KiB") == 1024
+    finally:
+        B.set_piece_bytes(65536)
+
+
+@pytest.mark.parametrize("kind", ["mixed", "text", "packets"])
+def test_long_streams_1mib_chunks_default_pieces(B, kind):
+    """BASELINE config 5's large end: 1 MiB chunks are cut into 64 KiB pieces by default."""
+    import torch
+    total, chunk = 96 << 20, 1 << 20
+    db = B.DeviceBatch(total, chunk)
+    db.fill({"mixed": B.CORPUS_MIXED, "text": B.CORPUS_TEXT, "packets": B.CORPUS_PACKET}[kind], 0x5EED0000 + 22)
+    before = B.lib().lzs_b200_kernel_launches()
+    db.compress()
+    assert B.lib().lzs_b200_kernel_launches() - before == 8
+    db.decompress()
+    torch.cuda.synchronize()
+    assert db.roundtrip_ok()
+    assert _compare_all_streams(B, db, "1 MiB chunks") == 96
+
+
+def test_one_large_buffer_through_the_drop_in_calls(B):
+    """What a caller of lzs.h does: ONE lzs_compress call on one large buffer (here 24 MiB with runs
+    of zeros of up to 3 MiB, text, records and noise in it) -- cut into pieces inside, one stream
+    outside, equal to the reference's; and a batch of three unequal long streams through the host
+    batch call."""
+    rng = np.random.default_rng(23)
+    parts = []
+    for i in range(40):
+        k = i % 5
+        if k == 0:
+            parts.append(bytes(int(rng.integers(1000, 3 << 20))))
+        elif k == 4:
+            parts.append(rng.integers(0, 256, int(rng.integers(1000, 300000)), dtype=np.uint8).tobytes())
+        else:
+            parts.append(helpers.corpus((helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_MIXED)[k - 1], 1,
+                                        int(rng.integers(1000, 900000)), first_index=i).tobytes())
+    big = b"".join(parts)[:24 << 20]
+    want = _reference_streams([big])[0]
+    got = B.lzs_compress(big)
+    assert got == want
+    assert B.lzs_decompress(got, len(big)) == big
+    three = [big[:5_000_001], big[5_000_001:5_700_000], big[9_000_000:9_000_000 + (3 << 20) + 17]]
+    assert B.compress_streams(three) == _reference_streams(three)
+    # a capacity smaller than the stream: the prefix that fits
+    assert B.compress_streams([three[1]], caps=[100_001]) == [_reference_streams([three[1]])[0][:100_001]]
+
+
+def test_long_streams_through_the_sliced_host_pipeline(B):
+    """More than eight ordered long streams take the host path's slices (upload / kernels / download
+    overlapped); the pieces' table is shared by the slices."""
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, (1 << 20) + 4099 * i, first_index=40 + i).tobytes() for i in range(12)]
+    got = B.compress_streams(data)
+    assert got == _reference_streams(data)
+    assert B.decompress_streams(got, [len(d) for d in data]) == data

@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Long streams (csrc/k23_pieces.cuh): device-resident compress GB/s of the 1 GiB mixed corpus in chunks
+of 128 KiB .. 1 GiB (ONE stream), with the streams cut into pieces of 32 / 64 / 128 KiB and uncut, and
+the drop-in single call lzs_compress() on one host buffer beside the unmodified reference on one
+host core.  Every cut result is compared with the uncut one (lengths and bytes).  One JSON line per row."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lzs-compression_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import lzs_b200 as B
+import helpers
+
+
+def timed(db, iters):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    best = 1e30
+    for _ in range(iters):
+        ev[0].record(); db.compress(); ev[1].record()
+        torch.cuda.synchronize()
+        best = min(best, ev[0].elapsed_time(ev[1]))
+    return best
+
+
+def main():
+    total = int(os.environ.get("PIECES_TOTAL_MIB", "1024")) << 20
+    quick = os.environ.get("PIECES_QUICK") == "1"
+    for kib in ((1024, total >> 10) if quick else (128, 256, 512, 1024, 16384, total >> 10)):
+        chunk = kib << 10
+        row = {"chunk_kib": kib, "streams": total // chunk}
+        want = None
+        for piece in ((0, 65536) if quick else (0, 32768, 65536, 131072)):
+            if piece == 0 and total // chunk < 64:
+                continue                      # uncut, one warp parses a whole stream: minutes
+            iters = 1 if piece == 0 and total // chunk < 1024 else 3
+            B.set_piece_bytes(piece)
+            db = B.DeviceBatch(total, chunk)
+            # the same bytes whatever the chunking: the 1 GiB mixed corpus of 64 KiB units
+            B.check(B.lib().lzs_b200_corpus_fill_device(db.raw.data_ptr(), 65536, 65536, 0, total // 65536, 0x5EED0002,
+                                                        B.CORPUS_MIXED, db._stream()))
+            before = B.lib().lzs_b200_kernel_launches()
+            ms = timed(db, iters)
+            cut = (B.lib().lzs_b200_kernel_launches() - before) // iters == 8
+            lens = db.comp_len.cpu().numpy().copy()
+            if want is None:
+                want = (lens, db.comp[:db.n * db.comp_stride].clone())
+            else:
+                assert (lens == want[0]).all(), "lengths differ with pieces of %d" % piece
+                a = db.comp[:db.n * db.comp_stride].view(db.n, db.comp_stride)
+                b = want[1].view(db.n, db.comp_stride)
+                if db.n <= 64:
+                    same = all(bool(torch.equal(a[k, :int(lens[k])], b[k, :int(lens[k])])) for k in range(db.n))
+                else:
+                    live = torch.arange(db.comp_stride, device=db.device)[None, :] < db.comp_len[:, None]
+                    same = not bool(((a != b) & live).any())
+                    del live
+                assert same, "bytes differ with pieces of %d" % piece
+                del a, b
+            row["piece_%d" % piece if piece else "uncut"] = {"ms": round(ms, 2), "gbs": round(total / ms / 1e6, 2), "cut": cut}
+            del db
+            torch.cuda.empty_cache()
+        del want
+        torch.cuda.empty_cache()
+        print(json.dumps(row), flush=True)
+    B.set_piece_bytes(65536)
+
+    # the drop-in call on one large host buffer
+    ref = helpers.reference() or helpers.oracle()
+    for mib in (1, 16, 256):
+        data = helpers.corpus(helpers.CORPUS_MIXED, mib * 16, 65536, first_index=7).tobytes()
+        B.lzs_compress(data[:1 << 20])
+        t0 = time.perf_counter(); got = B.lzs_compress(data); t_gpu = time.perf_counter() - t0
+        sample = data
+        t0 = time.perf_counter(); want = ref.compress(sample); t_cpu = time.perf_counter() - t0
+        assert got == want
+        print(json.dumps({"single_call_mib": mib, "lzs_compress_ms": round(t_gpu * 1e3, 2),
+                          "gbs": round(len(data) / t_gpu / 1e9, 3),
+                          "reference_one_core_gbs": round(len(sample) / t_cpu / 1e9, 3)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
