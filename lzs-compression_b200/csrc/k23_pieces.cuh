@@ -185,22 +185,29 @@ __device__ __forceinline__ void k23_token(uint32_t len, uint32_t off, uint32_t b
 }
 
 /* Whole warp: length of the match at p with offset loff, known to be >= 12, compared as far as
- * `limit` (<= n).  128 bytes per round, the loads of a round in flight together. */
+ * `limit` (<= n).  Most long matches end within the first 32 bytes; the ones that do not are
+ * compared 256 bytes per round, the loads of a round in flight together (a run through a whole
+ * file is measured by ONE warp, in the sweep: ~1 GB/s). */
 __device__ __forceinline__ uint32_t k23_long_length(const uint8_t *src, uint32_t p, uint32_t loff, uint32_t limit)
 {
     const uint32_t lane = lane_id();
     const uint8_t *from = src - loff;
     uint32_t       L = kSearchMax;
+    {
+        const uint32_t idx = p + L + lane;
+        const uint32_t ball = __ballot_sync(LZS_FULL_MASK, (idx < limit) && (src[idx] == from[idx]));
+        if (ball != LZS_FULL_MASK) return L + static_cast<uint32_t>(__ffs(static_cast<int>(~ball)) - 1);
+        L += 32u;
+    }
     for (;;) {
-        uint32_t ball[4];
+        uint32_t ball[8];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
+        for (int t = 0; t < 8; t++) {
             const uint32_t idx = p + L + lane + 32u * static_cast<uint32_t>(t);
-            const bool     same = (idx < limit) && (idx >= p) && (src[idx] == from[idx]);
-            ball[t] = __ballot_sync(LZS_FULL_MASK, same);
+            ball[t] = __ballot_sync(LZS_FULL_MASK, (idx < limit) && (src[idx] == from[idx]));
         }
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
+        for (int t = 0; t < 8; t++) {
             if (ball[t] != LZS_FULL_MASK) return L + static_cast<uint32_t>(__ffs(static_cast<int>(~ball[t])) - 1);
             L += 32u;
         }

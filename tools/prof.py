@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--compress-only", action="store_true", help="the whole compressor as one call (long streams are cut into pieces)")
     a = ap.parse_args()
     total = (a.mib << 20) // a.chunk * a.chunk
     if a.lanes:
@@ -36,6 +37,14 @@ def run(a, db, total):
     db.fill(KINDS[a.kind], 0x5EED0002)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    if a.compress_only:
+        for it in range(a.iters):
+            ev[0].record(); db.compress(); ev[1].record()
+            torch.cuda.synchronize()
+            if a.time:
+                t = ev[0].elapsed_time(ev[1])
+                print("%s chunk=%d iter %d: compress %.2f ms (%.1f GB/s)" % (a.kind, a.chunk, it, t, total / t / 1e6))
+        return
     for it in range(a.iters):
         ev[0].record(); db.match_only()
         ev[1].record(); db.parse_pack_only()

@@ -68,3 +68,12 @@ small.compress(); small.decompress(); torch.cuda.synchronize()
 B.lib().lzs_b200_set_force_safe_match(0)
 assert small.roundtrip_ok()
 print("sanitize workload (round 2 additions) ok")
+# long streams cut into pieces (csrc/k23_pieces.cuh): plan, K1 with look-ahead, spec, fix, sweep, pack
+B.set_piece_bytes(1024)
+long_data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 50000 + 13 * i, first_index=60 + i).tobytes() for i in range(3)]
+long_data += [b"\1" * 30000 + helpers.corpus(helpers.CORPUS_TEXT, 1, 9000, first_index=2).tobytes() + b"\0" * 20000, b"", b"x"]
+got = B.compress_streams(long_data)
+B.set_piece_bytes(65536)
+assert got == [o.compress(d) for d in long_data]
+assert B.compress_streams(long_data[:2], caps=[777, 0]) == [o.compress(long_data[0])[:777], b""]
+print("sanitize workload (pieces) ok")
