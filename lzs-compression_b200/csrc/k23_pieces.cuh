@@ -53,6 +53,8 @@ struct PieceTable {
     uint32_t *fix_exit, *fix_bits;     /* parse from the exit of the piece before                   */
     uint32_t *flags;      /* kPieceSpecOpen / kPieceFixOpen                                         */
     uint32_t *entry, *exit;            /* sweep: the true ones                                      */
+    uint32_t *run_end;    /* spec: 0, or the piece starts inside a long match (K1 length 12 at p0) whose bytes
+                             agree with those `offset` before them from p0 up to here                */
     uint32_t *first;      /* [n_streams + 1] first piece of every stream                            */
     uint32_t *count;      /* [0] pieces in use, [1] != 0: the table was too small, nothing is produced */
     uint32_t  cap;        /* entries                                                                */
@@ -60,7 +62,7 @@ struct PieceTable {
 constexpr uint32_t kPieceSpecOpen = 1u, kPieceFixOpen = 2u;
 constexpr uint32_t kPieceLookPieces = 4;      /* spec / fix compare at most this many pieces ahead  */
 constexpr uint32_t kPieceWalkMax = 2048;      /* fix gives up after this many tokens (sweep parses the piece instead) */
-constexpr size_t   kPieceEntryBytes = 2 * 8 + 13 * 4;
+constexpr size_t   kPieceEntryBytes = 2 * 8 + 14 * 4;
 
 __host__ __device__ inline size_t piece_table_bytes(uint32_t cap) { return static_cast<size_t>(cap) * kPieceEntryBytes + 256; }
 
@@ -86,6 +88,7 @@ __host__ __device__ inline PieceTable piece_table_at(void *base, uint32_t cap)
     t.flags = w;        w += cap;
     t.entry = w;        w += cap;
     t.exit = w;         w += cap;
+    t.run_end = w;      w += cap;
     t.first = w;
     t.cap = cap;
     return t;
@@ -188,11 +191,11 @@ __device__ __forceinline__ void k23_token(uint32_t len, uint32_t off, uint32_t b
  * `limit` (<= n).  Most long matches end within the first 32 bytes; the ones that do not are
  * compared 256 bytes per round, the loads of a round in flight together (a run through a whole
  * file is measured by ONE warp, in the sweep: ~1 GB/s). */
-__device__ __forceinline__ uint32_t k23_long_length(const uint8_t *src, uint32_t p, uint32_t loff, uint32_t limit)
+__device__ __forceinline__ uint32_t k23_long_length(const uint8_t *src, uint32_t p, uint32_t loff, uint32_t limit,
+                                                    uint32_t L = kSearchMax)
 {
     const uint32_t lane = lane_id();
     const uint8_t *from = src - loff;
-    uint32_t       L = kSearchMax;
     {
         const uint32_t idx = p + L + lane;
         const uint32_t ball = __ballot_sync(LZS_FULL_MASK, (idx < limit) && (src[idx] == from[idx]));
@@ -212,6 +215,35 @@ __device__ __forceinline__ uint32_t k23_long_length(const uint8_t *src, uint32_t
             L += 32u;
         }
     }
+}
+
+/* The same without a limit, for the sweep: a match that runs through many pieces (zeros, a period) is
+ * not compared byte by byte by this one warp.  Every piece that starts inside such a match has
+ * measured -- in spec, in parallel -- how far the bytes from ITS start agree at ITS offset
+ * (run_end); where that offset is ours, the agreement is the same fact, and the length jumps from
+ * piece to piece.  `first` is the stream's first entry in the table. */
+__device__ __forceinline__ uint32_t k23_long_length_hops(const uint8_t *src, const match_t *m, uint32_t n, uint32_t p,
+                                                         uint32_t loff, uint32_t piece, const uint32_t *run_end,
+                                                         uint32_t first)
+{
+    uint32_t q = p + kSearchMax;                       /* bytes in [p, q) are known to agree */
+    while (q < n) {
+        const uint32_t j = q / piece;
+        const uint32_t mv = m[j * piece];
+        if ((mv >> kMatchOffBits) >= kSearchMax && (mv & ((1u << kMatchOffBits) - 1u)) == loff) {
+            const uint32_t re = run_end[first + j];
+            if (re > q) {
+                q = re;
+                continue;
+            }
+        }
+        const uint64_t far = static_cast<uint64_t>(j + 1u) * piece;
+        const uint32_t bound = far < n ? static_cast<uint32_t>(far) : n;
+        const uint32_t q2 = p + k23_long_length(src, p, loff, bound, q - p);
+        if (q2 < bound) return q2 - p;
+        q = bound;
+    }
+    return umin32(q, n) - p;
 }
 
 /* bits of the nibbles that follow the first 1111 of a match of length L >= 8 */
@@ -272,13 +304,21 @@ __device__ __forceinline__ void pstage_emit_uniform(PieceStage &s, uint32_t val,
  * with kPack, writes them to the stage.  A long match is compared up to `limit`; if it is still
  * running there and the stream is not over, its end is `known_exit` (kPack: the sweep stored it) or
  * unknown (counting: returns false, exit and bits are then meaningless). */
+struct PieceHops {          /* sweep only: lets a long match jump over the pieces it runs through */
+    const uint32_t *run_end;
+    uint32_t        first, piece;
+};
+
 template <bool kPack>
 __device__ __forceinline__ bool k23_piece(const uint8_t *src, const match_t *m, uint32_t n, uint32_t pos, uint32_t p1,
                                           uint32_t limit, uint32_t known_exit, PieceStage &s, uint32_t &bits_out,
-                                          uint32_t &exit_out)
+                                          uint32_t &exit_out, uint32_t *first_run_end = nullptr,
+                                          const PieceHops *hops = nullptr)
 {
     const uint32_t lane = lane_id();
+    const uint32_t pos0 = pos;
     uint32_t       bits = 0;
+    if (first_run_end) *first_run_end = 0;
     while (pos < p1) {
         const uint32_t i = pos + lane;
         const bool     valid = i < p1;
@@ -304,17 +344,20 @@ __device__ __forceinline__ bool k23_piece(const uint8_t *src, const match_t *m, 
 
         uint32_t val = 0, nb = 0;
         if (tok) k23_token(len, off, byte, val, nb);
-        uint32_t incl = nb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(LZS_FULL_MASK, incl, static_cast<unsigned>(d));
-            if (lane >= static_cast<uint32_t>(d)) incl += v;
-        }
-        const uint32_t total = __shfl_sync(LZS_FULL_MASK, incl, 31);
+        uint32_t total;
         if (kPack) {
+            uint32_t incl = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(LZS_FULL_MASK, incl, static_cast<unsigned>(d));
+                if (lane >= static_cast<uint32_t>(d)) incl += v;
+            }
+            total = __shfl_sync(LZS_FULL_MASK, incl, 31);
             if (tok) stage_put(s.buf, s.cur + incl - nb, val, nb);
             s.cur += total;
             __syncwarp();
+        } else {
+            total = __reduce_add_sync(LZS_FULL_MASK, nb);      /* counting needs no per-token offsets */
         }
         bits += total;
 
@@ -326,7 +369,9 @@ __device__ __forceinline__ bool k23_piece(const uint8_t *src, const match_t *m, 
         if (last_long) {
             const uint32_t p = pos + static_cast<uint32_t>(last);
             const uint32_t loff = __shfl_sync(LZS_FULL_MASK, off, last);
-            uint32_t       L = k23_long_length(src, p, loff, limit);
+            uint32_t       L = hops ? k23_long_length_hops(src, m, n, p, loff, hops->piece, hops->run_end, hops->first)
+                                    : k23_long_length(src, p, loff, limit);
+            if (first_run_end && p == pos0) *first_run_end = p + L;
             if (p + L >= limit && limit < n) {               /* still running where the comparing stops */
                 if (!kPack) return false;
                 L = known_exit - p;
@@ -394,13 +439,14 @@ k23p_spec(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, c
     const uint32_t n = in_len[sid];
     const uint32_t p0 = t.p0[idx], p1 = p0 + t.len[idx];
     PieceStage     none = {};
-    uint32_t       bits = 0, exit = 0;
+    uint32_t       bits = 0, exit = 0, run_end = 0;
     const bool     ok = k23_piece<false>(in + in_off[sid], matches + in_off[sid], n, p0, p1, piece_limit(p1, n, piece), 0u,
-                                         none, bits, exit);
+                                         none, bits, exit, &run_end);
     if (lane_id() == 0) {
         t.spec_bits[idx] = bits;
         t.spec_exit[idx] = exit;
         t.flags[idx] = ok ? 0u : kPieceSpecOpen;
+        t.run_end[idx] = run_end;
     }
 }
 
@@ -477,7 +523,7 @@ k23p_fix(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, co
 __global__ void __launch_bounds__(kPieceThreads)
 k23p_sweep(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, const uint32_t *__restrict__ in_len,
            const match_t *__restrict__ matches, const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ out_len,
-           uint32_t n_streams, PieceTable t)
+           uint32_t n_streams, uint32_t piece, PieceTable t)
 {
     const uint32_t sid = blockIdx.x * kPieceWarps + (threadIdx.x >> 5);
     if (sid >= n_streams || t.count[1]) return;
@@ -517,8 +563,9 @@ k23p_sweep(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
                 bits = __shfl_sync(LZS_FULL_MASK, r_sb, static_cast<int>(k));
                 x = __shfl_sync(LZS_FULL_MASK, r_sx, static_cast<int>(k));
             } else {
-                PieceStage none = {};
-                k23_piece<false>(src, m, n, e, p1, n, 0u, none, bits, x);
+                PieceStage     none = {};
+                const PieceHops hops = {t.run_end, first, piece};
+                k23_piece<false>(src, m, n, e, p1, n, 0u, none, bits, x, nullptr, &hops);
             }
             if (lane == k) {
                 my_entry = e;

@@ -357,7 +357,7 @@ int compress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *i
     const unsigned sgrid = (n_streams + lzs::kPieceWarps - 1) / lzs::kPieceWarps;
     lzs::k23p_spec<<<pgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, piece, t);
     lzs::k23p_fix<<<pgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, piece, t);
-    lzs::k23p_sweep<<<sgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, out_cap, out_len, n_streams, t);
+    lzs::k23p_sweep<<<sgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, out_cap, out_len, n_streams, piece, t);
     lzs::k23p_pack<<<pgrid, lzs::kPieceThreads, 0, st>>>(in, in_off, in_len, matches, out, out_off, out_cap, t);
     g_launches += 4;
     CUDA_TRY(cudaGetLastError());

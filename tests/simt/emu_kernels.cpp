@@ -103,7 +103,7 @@ extern "C" int emu_compress_pieces(const uint8_t *in, const uint64_t *in_off, co
     simt::launch(dim3(pgrid), dim3(lzs::kPieceThreads), 0, [&] { lzs::k23p_spec(in, in_off, in_len, matches.data(), piece, t); });
     simt::launch(dim3(pgrid), dim3(lzs::kPieceThreads), 0, [&] { lzs::k23p_fix(in, in_off, in_len, matches.data(), piece, t); });
     simt::launch(dim3(sgrid), dim3(lzs::kPieceThreads), 0, [&] {
-        lzs::k23p_sweep(in, in_off, in_len, matches.data(), out_cap, out_len, n, t);
+        lzs::k23p_sweep(in, in_off, in_len, matches.data(), out_cap, out_len, n, piece, t);
     });
     simt::launch(dim3(pgrid), dim3(lzs::kPieceThreads), 0, [&] {
         lzs::k23p_pack(in, in_off, in_len, matches.data(), out, out_off, out_cap, t);

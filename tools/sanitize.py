@@ -73,7 +73,8 @@ B.set_piece_bytes(1024)
 long_data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 50000 + 13 * i, first_index=60 + i).tobytes() for i in range(3)]
 long_data += [b"\1" * 30000 + helpers.corpus(helpers.CORPUS_TEXT, 1, 9000, first_index=2).tobytes() + b"\0" * 20000, b"", b"x"]
 got = B.compress_streams(long_data)
+cut = B.compress_streams(long_data[:2], caps=[777, 0])
 B.set_piece_bytes(65536)
 assert got == [o.compress(d) for d in long_data]
-assert B.compress_streams(long_data[:2], caps=[777, 0]) == [o.compress(long_data[0])[:777], b""]
+assert cut == [o.compress(long_data[0])[:777], b""]
 print("sanitize workload (pieces) ok")

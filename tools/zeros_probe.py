@@ -1,0 +1,15 @@
+#!/usr/bin/env python3
+"""One lzs_compress call on a buffer of zeros (one match through the whole stream: the worst case of the
+piece path, measured by one warp in the sweep) beside the unmodified reference on one host core."""
+import sys, time, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lzs-compression_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, lzs_b200 as B, helpers
+ref = helpers.reference() or helpers.oracle()
+for mib in (64, 512):
+    data = bytes(mib << 20)
+    B.lzs_compress(data[:1 << 20])
+    t0 = time.perf_counter(); got = B.lzs_compress(data); t1 = time.perf_counter()
+    want = ref.compress(data); t2 = time.perf_counter()
+    assert got == want
+    print("zeros %d MiB: lzs_compress %.1f ms, reference %.1f ms, %d bytes" % (mib, (t1 - t0) * 1e3, (t2 - t1) * 1e3, len(got)), flush=True)
