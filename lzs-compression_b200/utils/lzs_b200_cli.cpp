@@ -1,7 +1,7 @@
 /*
  * lzs-b200 -- file compressor / decompressor over the batch ABI.
  *
- *   lzs-b200 c [-b chunk_bytes] [-x index_file] infile outfile
+ *   lzs-b200 c [-b chunk_bytes | -s] [-x index_file] infile outfile
  *   lzs-b200 d [-x index_file] infile outfile
  *
  * The reference's file format is a raw LZS stream with no header (c/src/utils/lzs-compress.c:82-134
@@ -9,8 +9,10 @@
  * lzs_decompress_incremental).  Its decoder keeps going after an end marker
  * (lzs-decompression.c:564-576), so a file made of back-to-back INDEPENDENT streams, one per chunk,
  * is a valid input for the reference's lzs-decompress -- and that is what `c` writes, because
- * independent chunks are what the GPU compresses in parallel.  With a chunk size of at least the
- * file size the output is the single stream the reference's lzs-compress writes, byte for byte.
+ * independent chunks are what both the compressor and the decoder of the GPU take in parallel.
+ * With `-s` (or a chunk size of at least the file size) the output is the single stream the
+ * reference's lzs-compress writes, byte for byte; the library compresses it in parallel all the
+ * same (cut into pieces inside, csrc/k23_pieces.cuh), but nobody can DEcode one stream in parallel.
  *
  * Finding the stream starts again needs a scan of the whole bit stream, so `c -x` also writes a
  * small index (one (uncompressed, compressed) length pair per chunk) and `d -x` uses it to decode
@@ -58,7 +60,7 @@ bool write_file(const char *path, const uint8_t *data, size_t n)
 
 int usage()
 {
-    fprintf(stderr, "usage: lzs-b200 c [-b chunk_bytes] [-x index_file] infile outfile\n"
+    fprintf(stderr, "usage: lzs-b200 c [-b chunk_bytes | -s] [-x index_file] infile outfile\n"
                     "       lzs-b200 d [-x index_file] infile outfile\n");
     return 2;
 }
@@ -189,6 +191,9 @@ int main(int argc, char **argv)
         if (strcmp(argv[a], "-b") == 0 && a + 1 < argc) {
             chunk = strtoull(argv[a + 1], nullptr, 0);
             a += 2;
+        } else if (strcmp(argv[a], "-s") == 0) {        /* one stream: the reference's own file */
+            chunk = 0xFFFFFF00ull;
+            a += 1;
         } else if (strcmp(argv[a], "-x") == 0 && a + 1 < argc) {
             index_path = argv[a + 1];
             a += 2;

@@ -110,3 +110,19 @@ def test_file_cli_single_chunk_equals_reference_compressor(tmp_path):
         back = tmp_path / (tag + ".back")
         _run(_cli(), "d", str(theirs), str(back))
         assert back.read_bytes() == data, tag
+
+
+def test_file_cli_single_stream_of_a_large_file_equals_reference_compressor(tmp_path):
+    """`lzs-b200 c -s` on a 12 MiB file: ONE stream, compressed in parallel inside the library (cut into
+    pieces, csrc/k23_pieces.cuh), byte for byte the file the reference's own lzs-compress writes -- and the
+    reference's lzs-decompress restores the input from it."""
+    data = b"".join(helpers.corpus(kind, 1, 3 << 20, seed=0x5EED0000 + 30 + kind).tobytes()
+                    for kind in (helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_MIXED)) + bytes(3 << 20) + b"tail"
+    src = tmp_path / "big.bin"
+    src.write_bytes(data)
+    ours, theirs, back = tmp_path / "big.b200.lzs", tmp_path / "big.ref.lzs", tmp_path / "big.back"
+    _run(_cli(), "c", "-s", str(src), str(ours))
+    _run(_bin("ref-lzs-compress"), str(src), str(theirs))
+    assert ours.read_bytes() == theirs.read_bytes()
+    _run(_bin("ref-lzs-decompress"), str(ours), str(back))
+    assert back.read_bytes() == data

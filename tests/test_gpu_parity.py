@@ -584,6 +584,9 @@ def test_one_large_buffer_through_the_drop_in_calls(B):
     assert B.compress_streams(three) == _reference_streams(three)
     # a capacity smaller than the stream: the prefix that fits
     assert B.compress_streams([three[1]], caps=[100_001]) == [_reference_streams([three[1]])[0][:100_001]]
+    # around the size from which one buffer is cut (two pieces of 64 KiB), and piece borders +- 1
+    for n in (131071, 131072, 131073, 196607, 196608, 196609, 262145):
+        assert B.lzs_compress(big[7_000_000:7_000_000 + n]) == _reference_streams([big[7_000_000:7_000_000 + n]])[0], n
 
 
 def test_long_streams_through_the_sliced_host_pipeline(B):
