@@ -19,3 +19,7 @@ timeout 900 python tools/sweep.py > gpurun_out/${R}_sweep.jsonl 2> gpurun_out/${
 ls -la gpurun_out | tail -12
 timeout 600 python tools/inc_device_bench.py --flows 1048576 --sample 256 > gpurun_out/${R}_incremental_device.json 2> gpurun_out/${R}_incremental_device.err; cat gpurun_out/${R}_incremental_device.json
 timeout 300 python tools/flows_bench.py > gpurun_out/${R}_flows_bulk.json 2> gpurun_out/${R}_flows_bulk.err; cat gpurun_out/${R}_flows_bulk.json
+timeout 400 python tools/pieces_bench.py > gpurun_out/${R}_pieces_bench.jsonl 2> gpurun_out/${R}_pieces_bench.err; cut -c1-200 gpurun_out/${R}_pieces_bench.jsonl
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${R}_pieces_launches.csv \
+    python tools/prof.py --mib 1024 --chunk 1048576 --iters 2 --compress-only > /dev/null 2>&1
+timeout 200 python tools/zeros_probe.py 2>&1 | tail -2
