@@ -136,12 +136,16 @@ k23_parse_pack(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
         /* K2: token starts reachable from lane 0 inside this group */
         uint32_t j = (is_long || !valid) ? 32u : umin32(nxt, 32u);
         uint32_t reach = 1u;
+        if (__any_sync(LZS_FULL_MASK, len >= kMinLen)) {
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const uint32_t c = (((reach >> lane) & 1u) && j < 32u) ? (1u << j) : 0u;
-            reach |= __reduce_or_sync(LZS_FULL_MASK, c);
-            const uint32_t jj = __shfl_sync(LZS_FULL_MASK, j, static_cast<int>(j & 31u));
-            j = (j < 32u) ? jj : 32u;
+            for (int r = 0; r < 5; r++) {
+                const uint32_t c = (((reach >> lane) & 1u) && j < 32u) ? (1u << j) : 0u;
+                reach |= __reduce_or_sync(LZS_FULL_MASK, c);
+                const uint32_t jj = __shfl_sync(LZS_FULL_MASK, j, static_cast<int>(j & 31u));
+                j = (j < 32u) ? jj : 32u;
+            }
+        } else {
+            reach = 0xFFFFFFFFu;            /* literals only (incompressible data): every position starts a token */
         }
         const uint32_t nvalid = umin32(32u, n - pos);
         if (nvalid < 32u) reach &= (1u << nvalid) - 1u;
