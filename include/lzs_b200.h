@@ -256,6 +256,19 @@ int lzs_b200_set_force_safe_match(int on);
  * lzs_compress / lzs_simple_compress; the decoder has no counterpart. */
 int lzs_b200_set_piece_bytes(uint32_t bytes);
 
+/* The decoder's counterpart (csrc/k4_pieces.cuh).  Where the tokens of a stream start is found in
+ * parallel inside the stream (pieces of `bytes` COMPRESSED bytes, default 2048, environment
+ * LZS_B200_DPIECE, 0 = off), literals go straight to their place and the matches are replayed in
+ * order by one warp per stream -- the one serial step that is left, a copy per match instead of a
+ * bit parser.  Used by lzs_b200_decompress_batch_device / _status_batch_device for batches of at most
+ * 4096 streams whose scratch has room for the piece table, i.e. was sized with
+ * lzs_b200_decompress_scratch_bytes_long(in_span, n_streams) (in_span = compressed bytes covered by the
+ * batch); with less scratch every stream is decoded by one group of lanes, as before.  The host batch
+ * call and lzs_decompress do this themselves.  Malformed streams and outputs that are too small
+ * come out exactly as before: the piece passes hand such streams to the serial decoder. */
+size_t lzs_b200_decompress_scratch_bytes_long(uint64_t in_span, uint32_t n_streams);
+int    lzs_b200_set_decode_piece_bytes(uint32_t bytes);
+
 /* Number of kernels launched by this library in the calling process so far. */
 uint64_t lzs_b200_kernel_launches(void);
 

@@ -84,8 +84,12 @@ k4_decode(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
           const uint32_t *__restrict__ in_len, uint8_t *__restrict__ out,
           const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
           uint32_t *__restrict__ out_len, uint32_t n_streams, uint32_t *__restrict__ next_stream,
-          uint8_t *__restrict__ status, const uint32_t *__restrict__ order, const uint32_t *__restrict__ hist_len)
+          uint8_t *__restrict__ status, const uint32_t *__restrict__ order, const uint32_t *__restrict__ hist_len,
+          const uint32_t *__restrict__ n_dev = nullptr)
 {
+    /* a list of streams made on the device (k4_pieces.cuh: the streams its passes left to this kernel):
+     * `order` holds the list, *n_dev its length, n_streams only bounds the grid */
+    if (n_dev != nullptr) n_streams = *n_dev;
     LZS_DYN_SMEM(uint8_t, smem);
     const uint32_t lane = lane_id();
     const uint32_t gl = lane % G;

@@ -24,6 +24,7 @@
 #include "k23_parse_pack.cuh"
 #include "k23_pieces.cuh"
 #include "k4_decode.cuh"
+#include "k4_pieces.cuh"
 
 namespace {
 
@@ -33,6 +34,7 @@ std::atomic<int>           g_decode_lanes{0};
 std::atomic<int>           g_force_safe_match{0};
 std::atomic<int>           g_zero_copy_out{-1};   /* -1: read LZS_B200_ZEROCOPY on first use */
 std::atomic<int64_t>       g_piece_bytes{-1};     /* -1: read LZS_B200_PIECE on first use; 0: long streams are never cut */
+std::atomic<int64_t>       g_dpiece_bytes{-1};    /* the same for the decoder (LZS_B200_DPIECE), compressed bytes per piece */
 
 int fail(int code, const char *fmt, ...)
 {
@@ -141,6 +143,23 @@ uint32_t piece_table_entries(uint64_t in_span, uint32_t piece)
     const uint64_t e = in_span / piece + in_span / (2ull * piece) + 16u;
     return e > 0x7FFFFFFFull ? 0x7FFFFFFFu : static_cast<uint32_t>(e);
 }
+/* The decoder's pieces (k4_pieces.cuh) are pieces of the COMPRESSED stream.  LZS_B200_DPIECE sets their
+ * size (0: long streams are decoded by one group of lanes each, as short ones are). */
+uint32_t dpiece_bytes()
+{
+    int64_t v = g_dpiece_bytes.load();
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_DPIECE");
+        v = e ? atoll(e) : 2048;                         /* measured: 2048 / 4096 / 8192 -> 25.3 / 27.6 / 35.9 ms per GiB in 1 MiB chunks */
+        if (v < 0 || v > (1ll << 24)) v = 2048;
+        if (v != 0 && v < 16) v = 16;
+        g_dpiece_bytes.store(v);
+    }
+    return static_cast<uint32_t>(v);
+}
+constexpr uint32_t kCutStreamsMaxDecode = 4096;
+size_t order_bytes(uint32_t n_streams) { return align_up(static_cast<size_t>(n_streams) * sizeof(uint32_t), 256); }
+
 size_t matches_bytes(uint64_t in_span) { return align_up(static_cast<size_t>(in_span) * sizeof(lzs::match_t) + 64, 256); }
 /* Cut the streams of this batch?  Decided from what the host knows without looking at the lengths:
  * few streams (one warp per stream fills the parse kernel from ~2000 streams on: measured, 1 GiB in
@@ -304,7 +323,23 @@ size_t lzs_b200_decompress_scratch_bytes(void) { return kCounterBytes; }
 /* with room for the launch order of n streams (see k4_decode.cuh) */
 size_t lzs_b200_decompress_scratch_bytes_for(uint32_t n_streams)
 {
-    return kCounterBytes + align_up(static_cast<size_t>(n_streams) * sizeof(uint32_t), 256);
+    return kCounterBytes + order_bytes(n_streams);
+}
+
+/* with room for the piece table of a batch of few long streams (k4_pieces.cuh): in_span compressed bytes */
+size_t lzs_b200_decompress_scratch_bytes_long(uint64_t in_span, uint32_t n_streams)
+{
+    const uint32_t piece = dpiece_bytes();
+    if (piece == 0 || n_streams > kCutStreamsMaxDecode) return lzs_b200_decompress_scratch_bytes_for(n_streams);
+    const uint64_t cap = in_span / piece + 2ull * n_streams + 16u;
+    return kCounterBytes + order_bytes(n_streams) + align_up(lzs::dpiece_table_bytes(static_cast<uint32_t>(cap > 0x7FFFFFFFull ? 0x7FFFFFFFull : cap), piece), 256);
+}
+
+int lzs_b200_set_decode_piece_bytes(uint32_t bytes)
+{
+    if (bytes != 0 && (bytes < 16 || bytes > (1u << 24))) return fail(LZS_B200_EINVAL, "piece size must be 0 or 16 .. 2^24");
+    g_dpiece_bytes.store(bytes);
+    return LZS_B200_OK;
 }
 
 }  // extern "C"
@@ -362,6 +397,64 @@ int compress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *i
     g_launches += 4;
     CUDA_TRY(cudaGetLastError());
     return LZS_B200_OK;
+}
+
+/* k4_decode over n_streams streams, or over the list `order` whose length *n_dev the device knows
+ * (grid_streams bounds it) */
+int launch_k4(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out, const uint64_t *out_off,
+              const uint32_t *out_cap, uint32_t *out_len, uint32_t n_streams, uint32_t *counter, uint8_t *status,
+              const uint32_t *order, const uint32_t *hist_len, const uint32_t *n_dev, uint32_t grid_streams, cudaStream_t st,
+              DeviceInfo *d)
+{
+    const int lanes = decode_lanes();
+    const int idx = lanes == 4 ? 0 : lanes == 8 ? 1 : lanes == 16 ? 2 : 3;
+    const unsigned per_block = lzs::kDecThreads / lanes;
+    unsigned       want = (grid_streams + per_block - 1) / per_block;
+    unsigned       resident = static_cast<unsigned>(d->sms) * static_cast<unsigned>(d->dec_blocks[idx] > 0 ? d->dec_blocks[idx] : 1);
+    const unsigned grid = want < resident ? want : resident;
+    switch (lanes) {
+        case 4:
+            lzs::k4_decode<4><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<4>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len, n_dev);
+            break;
+        case 16:
+            lzs::k4_decode<16><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<16>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len, n_dev);
+            break;
+        case 32:
+            lzs::k4_decode<32><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<32>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len, n_dev);
+            break;
+        default:
+            lzs::k4_decode<8><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<8>(), st>>>(
+                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len, n_dev);
+            break;
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LZS_B200_OK;
+}
+
+/* The decoder for few long streams: the passes of k4_pieces.cuh, then k4_decode for the streams they
+ * left (malformed, short of output): a launch that ends at once when there are none. */
+int decompress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                      const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint8_t *status,
+                      uint32_t n_streams, uint32_t piece, uint32_t cap, void *table_mem, cudaStream_t st, DeviceInfo *d)
+{
+    const lzs::DPieceTable t = lzs::dpiece_table_at(table_mem, cap, piece);
+    const unsigned pgrid = (cap + 127u) / 128u, sgrid = (n_streams + 3u) / 4u;
+    lzs::k4p_plan<<<1, 1024, 0, st>>>(in_len, n_streams, piece, t);
+    lzs::k4p_spec<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, t);
+    lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 0u, t);
+    lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 1u, t);
+    lzs::k4p_sweep<<<sgrid, 128, 0, st>>>(in, in_off, in_len, out_cap, out_len, status, n_streams, piece, t);
+    lzs::k4p_emit<<<pgrid, 128, 0, st>>>(in, in_off, in_len, out, out_off, n_streams, piece, t);
+    lzs::k4p_copy<<<sgrid, 128, 0, st>>>(out, out_off, out_len, n_streams, t);
+    lzs::k4p_dirty_list<<<(n_streams + 127u) / 128u, 128, 0, st>>>(n_streams, t);
+    g_launches += 8;
+    CUDA_TRY(cudaGetLastError());
+    return launch_k4(in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, t.count + 3, status, t.dirty_list, nullptr,
+                     t.count + 2, n_streams, st, d);
 }
 }  // namespace
 
@@ -497,6 +590,18 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t    *counter = static_cast<uint32_t *>(scratch);
     CUDA_TRY(cudaMemsetAsync(counter, 0, kCounterBytes, st));
+    /* few long streams, and scratch with room for a piece table (lzs_b200_decompress_scratch_bytes_long):
+     * token starts found in parallel inside the streams, k4_pieces.cuh */
+    const uint32_t dpiece = dpiece_bytes();
+    const size_t   fixed = kCounterBytes + order_bytes(n_streams);
+    if (dpiece != 0 && hist_len == nullptr && n_streams <= kCutStreamsMaxDecode && scratch_bytes > fixed + 4096) {
+        const size_t   per_piece = 4u * (lzs::kDPieceEntryWords + lzs::dpiece_record_stride(dpiece));
+        const uint64_t fit = (scratch_bytes - fixed - 512) / per_piece;
+        const uint32_t cap = fit > 0x7FFFFFFFull ? 0x7FFFFFFFu : static_cast<uint32_t>(fit);
+        if (cap >= 2u * n_streams + 16u)
+            return decompress_pieces(in, in_off, in_len, out, out_off, out_cap, out_len, status, n_streams, dpiece, cap,
+                                     static_cast<uint8_t *>(scratch) + fixed, st, d);
+    }
     /* launch order: streams of similar density together, the fastest kind last (k4_decode.cuh);
      * needs scratch for one index per stream, otherwise the streams go in index order */
     const uint32_t *order = nullptr;
@@ -509,33 +614,9 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
         g_launches += 2;
         order = ord;
     }
-    const int lanes = decode_lanes();
-    const int idx = lanes == 4 ? 0 : lanes == 8 ? 1 : lanes == 16 ? 2 : 3;
-    const unsigned per_block = lzs::kDecThreads / lanes;
-    unsigned       want = (n_streams + per_block - 1) / per_block;
-    unsigned       resident = static_cast<unsigned>(d->sms) * static_cast<unsigned>(d->dec_blocks[idx] > 0 ? d->dec_blocks[idx] : 1);
-    const unsigned grid = want < resident ? want : resident;
-    switch (lanes) {
-        case 4:
-            lzs::k4_decode<4><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<4>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
-            break;
-        case 16:
-            lzs::k4_decode<16><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<16>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
-            break;
-        case 32:
-            lzs::k4_decode<32><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<32>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
-            break;
-        default:
-            lzs::k4_decode<8><<<grid, lzs::kDecThreads, lzs::k4_smem_bytes<8>(), st>>>(
-                in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len);
-            break;
-    }
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    return LZS_B200_OK;
+    rc = launch_k4(in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, counter, status, order, hist_len, nullptr,
+                   n_streams, st, d);
+    return rc;
 }
 
 int lzs_b200_corpus_fill_device(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
@@ -956,7 +1037,13 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     HostPath     &p = *hp;
     PipelineScope scope(p);                 /* declared after the lock: drains before the arena is released */
     cudaStream_t  st = p.stream;
-    const size_t  scratch = decompress ? lzs_b200_decompress_scratch_bytes_for(n) : lzs_b200_compress_scratch_bytes(in_span);
+    /* few long streams to decode: one call with room for the piece table (k4_pieces.cuh) instead of the
+     * slices, whose streams would each be decoded by one group of lanes */
+    const bool    long_decode = decompress && dpiece_bytes() != 0 && n <= kCutStreamsMaxDecode &&
+                             static_cast<uint64_t>(n) * 2u * dpiece_bytes() <= in_span;
+    const size_t  scratch = decompress ? (long_decode ? lzs_b200_decompress_scratch_bytes_long(in_span, n)
+                                                      : lzs_b200_decompress_scratch_bytes_for(n))
+                                       : lzs_b200_compress_scratch_bytes(in_span);
     /* A decoder writes every output byte exactly once and reads none back (its history is in shared
      * memory), so when the caller's output buffer is pinned and device mapped it CAN decode straight
      * into it over PCIe (option, off by default: see mapped_host_range). */
@@ -987,7 +1074,7 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
      * overlap: slice k uploads and computes on work[k % 8] (the decoder needs several
      * slices resident at once to fill the GPU), finished slices are downloaded on `down`, and
      * only the bytes a slice really produced come back. */
-    bool ordered = n > 8;
+    bool ordered = n > 8 && !long_decode;
     for (uint32_t s2 = 1; s2 < n && ordered; s2++)
         ordered = in_off[s2] >= in_off[s2 - 1] + in_len[s2 - 1] && out_off[s2] >= out_off[s2 - 1] + out_cap[s2 - 1];
     if (ordered) {

@@ -84,6 +84,9 @@ def lib():
                                               ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp]
     L.lzs_b200_set_decode_lanes.argtypes = [ctypes.c_int]
     L.lzs_b200_set_piece_bytes.argtypes = [ctypes.c_uint32]
+    L.lzs_b200_set_decode_piece_bytes.argtypes = [ctypes.c_uint32]
+    L.lzs_b200_decompress_scratch_bytes_long.restype = ctypes.c_size_t
+    L.lzs_b200_decompress_scratch_bytes_long.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
     L.lzs_b200_pack_streams_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
     L.lzs_b200_pack_streams_peers_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
     L.lzs_b200_pack_streams_multicast_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
@@ -243,6 +246,11 @@ def set_piece_bytes(n):
     check(lib().lzs_b200_set_piece_bytes(int(n)))
 
 
+def set_decode_piece_bytes(n):
+    """Compressed bytes per piece in the decoder for long streams (lzs_b200_set_decode_piece_bytes); 0 = off."""
+    check(lib().lzs_b200_set_decode_piece_bytes(int(n)))
+
+
 class DeviceBatch:
     """Device-resident uniform chunking of one torch.uint8 buffer (plumbing only:
     torch provides the allocations and the stream; all work is in liblzs.so)."""
@@ -267,7 +275,8 @@ class DeviceBatch:
         self.raw = torch.empty(self.total + 64, dtype=torch.uint8, device=self.device)
         self.comp = torch.empty(self.n * self.comp_stride + 64, dtype=torch.uint8, device=self.device)
         self.dec = torch.empty(self.total + 64, dtype=torch.uint8, device=self.device)
-        nscratch = lib().lzs_b200_compress_scratch_bytes(self.total)
+        nscratch = max(lib().lzs_b200_compress_scratch_bytes(self.total),
+                       lib().lzs_b200_decompress_scratch_bytes_long(self.n * self.comp_stride, self.n))
         self.scratch = torch.empty(nscratch, dtype=torch.uint8, device=self.device)
 
     def _stream(self):

@@ -141,6 +141,27 @@ def compress_pieces(streams, piece, caps=None, grid=1, align=16, lead=0, out_lea
     return _collect(dst, out_off, caps, out_len, "packer"), stats
 
 
+def decode_pieces(streams, caps, piece, align=16, lead=0, out_lead=0, cap_entries=None, with_status=False):
+    """The decoder for long streams (csrc/k4_pieces.cuh): compressed streams cut into pieces of `piece`
+    bytes, dirty streams finished by k4_decode.  Returns (outputs, stats[, status]) with stats = [pieces,
+    dirty streams, pieces fix left open, table overflow]."""
+    src, in_off, in_len = pack_streams(streams, align, lead)
+    dst, out_off, out_cap = _out_layout(caps, out_lead)
+    out_len = np.zeros(len(streams), dtype=np.uint32)
+    status = np.zeros(max(len(streams), 1), dtype=np.uint8)
+    stats = np.zeros(4, dtype=np.uint32)
+    if cap_entries is None:
+        cap_entries = sum(max(1, -(-len(s) // piece)) for s in streams) + len(streams) + 3
+    L = lib()
+    L.emu_decode_pieces.argtypes = [c_u8p, c_u64p, c_u32p, c_u8p, c_u64p, c_u32p, c_u32p, ctypes.c_uint32,
+                                    ctypes.c_uint32, ctypes.c_uint32, c_u8p, c_u32p]
+    L.emu_decode_pieces(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(dst), _ptr(out_off, c_u64p),
+                        _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams), piece, cap_entries, _ptr(status),
+                        _ptr(stats, c_u32p))
+    got = _collect(dst, out_off, caps, out_len, "decoder")
+    return (got, stats, status[:len(streams)]) if with_status else (got, stats)
+
+
 # ---- flows with kept history (lzs_b200_*_flows_batch_device on the emulator) ----
 
 def flows_layout(flows, lead=0):

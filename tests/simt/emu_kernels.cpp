@@ -10,6 +10,7 @@
 #include "../../lzs-compression_b200/csrc/k23_parse_pack.cuh"
 #include "../../lzs-compression_b200/csrc/k23_pieces.cuh"
 #include "../../lzs-compression_b200/csrc/k4_decode.cuh"
+#include "../../lzs-compression_b200/csrc/k4_pieces.cuh"
 
 template <int G>
 static void run_decode(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
@@ -118,6 +119,38 @@ extern "C" int emu_compress_pieces(const uint8_t *in, const uint64_t *in_off, co
         }
     }
     return static_cast<int>(t.count[1]);
+}
+
+/* The decoder for long streams (k4_pieces.cuh), the launches of decompress_pieces() in lzs_b200.cu one
+ * after the other, the k4_decode launch for the dirty streams included.  stats (4 words): pieces,
+ * dirty streams, pieces fix left open, table overflow. */
+extern "C" int emu_decode_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                                 const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
+                                 uint32_t piece, uint32_t cap, uint8_t *status, uint32_t *stats)
+{
+    std::vector<uint32_t> mem(lzs::dpiece_table_bytes(cap, piece) / 4 + 16, 0xCDCDCDCDu);
+    const lzs::DPieceTable t = lzs::dpiece_table_at(mem.data(), cap, piece);
+    const unsigned pgrid = (cap + 127) / 128, sgrid = (n + 3) / 4;
+    simt::launch(dim3(1), dim3(1024), 0, [&] { lzs::k4p_plan(in_len, n, piece, t); });
+    simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_spec(in, in_off, in_len, n, piece, t); });
+    simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 0u, t); });
+    simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 1u, t); });
+    simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_sweep(in, in_off, in_len, out_cap, out_len, status, n, piece, t); });
+    simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_emit(in, in_off, in_len, out, out_off, n, piece, t); });
+    simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_copy(out, out_off, out_len, n, t); });
+    simt::launch(dim3((n + 127) / 128), dim3(128), 0, [&] { lzs::k4p_dirty_list(n, t); });
+    simt::launch(dim3(2), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<8>(), [&] {
+        lzs::k4_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &t.count[3], status, t.dirty_list, nullptr,
+                          &t.count[2]);
+    });
+    if (stats) {
+        stats[0] = t.count[0];
+        stats[1] = t.count[2];
+        stats[2] = 0;
+        for (uint32_t i = 0; i < t.count[0]; i++) stats[2] += t.fix_status[i] == lzs::kDStOpen;
+        stats[3] = t.count[1];
+    }
+    return 0;
 }
 
 #include "../../lzs-compression_b200/csrc/incremental.cuh"

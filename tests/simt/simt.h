@@ -348,6 +348,7 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -596,3 +596,87 @@ def test_long_streams_through_the_sliced_host_pipeline(B):
     got = B.compress_streams(data)
     assert got == _reference_streams(data)
     assert B.decompress_streams(got, [len(d) for d in data]) == data
+
+
+# ---------------------------------------------------------------- the decoder for long streams (csrc/k4_pieces.cuh)
+
+def test_long_streams_decoder_small_pieces(B):
+    """Token starts found in parallel inside the streams: pieces of 256 compressed bytes put ~180 borders
+    into every stream of a 64 MiB batch of 64 KiB chunks.  The launch counter says the piece passes ran."""
+    import torch
+    B.set_decode_piece_bytes(256)
+    try:
+        db = B.DeviceBatch(64 << 20, 65536)
+        db.fill(B.CORPUS_MIXED, 0x5EED0000 + 31)
+        db.compress()
+        before = B.lib().lzs_b200_kernel_launches()
+        db.decompress()
+        assert B.lib().lzs_b200_kernel_launches() - before == 9   # plan, spec, fix x2, sweep, emit, copy, dirty list, k4_decode for the dirty
+        torch.cuda.synchronize()
+        assert db.roundtrip_ok()
+    finally:
+        B.set_decode_piece_bytes(2048)
+
+
+@pytest.mark.parametrize("kind", ["mixed", "text", "random"])
+def test_long_streams_decoder_1mib_chunks(B, kind):
+    import torch
+    db = B.DeviceBatch(96 << 20, 1 << 20)
+    db.fill({"mixed": B.CORPUS_MIXED, "text": B.CORPUS_TEXT, "random": B.CORPUS_RANDOM}[kind], 0x5EED0000 + 32)
+    db.compress()
+    before = B.lib().lzs_b200_kernel_launches()
+    db.decompress()
+    assert B.lib().lzs_b200_kernel_launches() - before == 9
+    torch.cuda.synchronize()
+    assert db.roundtrip_ok()
+
+
+def test_long_streams_decoder_leaves_dirty_streams_to_the_serial_decoder(B):
+    """Damaged streams, random bits, outputs that are too small, runs of zeros and clean streams in ONE
+    batch through the piece passes (pieces of 16 bytes): bytes and lengths as the reference gives them."""
+    ref = helpers.reference() or helpers.oracle()
+    rng = np.random.default_rng(41)
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, int(rng.integers(200, 9000)), first_index=i).tobytes() for i in range(60)]
+    data += [bytes(70000), b"ab" * 30000, b""]
+    comp = [ref.compress(d) for d in data]
+    streams, caps = [], []
+    for i, (c, d) in enumerate(zip(comp, data)):
+        k = i % 5
+        if k == 0:   streams.append(c); caps.append(len(d))                     # clean, output exactly full
+        elif k == 1: streams.append(c); caps.append(len(d) + 50)                # clean
+        elif k == 2: streams.append(c[:len(c) // 2]); caps.append(len(d))       # cut off
+        elif k == 3: streams.append(c); caps.append(len(d) // 3)                # output too small
+        else:
+            bad = bytearray(c)
+            if bad: bad[len(bad) // 3] ^= 0x5A
+            streams.append(bytes(bad)); caps.append(len(d) + 100)               # damaged
+    streams += [rng.integers(0, 256, 300, dtype=np.uint8).tobytes() for _ in range(20)]
+    caps += [2000] * 20
+    B.set_decode_piece_bytes(16)
+    try:
+        got = B.decompress_streams(streams, caps)
+    finally:
+        B.set_decode_piece_bytes(2048)
+    for i, (s, c, g) in enumerate(zip(streams, caps, got)):
+        assert g == ref.decompress(s, c), i
+
+
+def test_one_large_buffer_decoded_through_the_drop_in_call(B):
+    """lzs_decompress on ONE stream of 24 MiB (text, records, noise, runs of zeros of up to 3 MiB)."""
+    rng = np.random.default_rng(23)
+    parts = []
+    for i in range(40):
+        k = i % 5
+        if k == 0:
+            parts.append(bytes(int(rng.integers(1000, 3 << 20))))
+        elif k == 4:
+            parts.append(rng.integers(0, 256, int(rng.integers(1000, 300000)), dtype=np.uint8).tobytes())
+        else:
+            parts.append(helpers.corpus((helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_MIXED)[k - 1], 1,
+                                        int(rng.integers(1000, 900000)), first_index=i).tobytes())
+    big = b"".join(parts)[:24 << 20]
+    comp = _reference_streams([big])[0]
+    assert B.lzs_decompress(comp, len(big)) == big
+    assert B.lzs_decompress(comp, len(big) + 1000) == big
+    assert B.lzs_decompress(comp, 1 << 20) == big[:1 << 20]                      # too small: the serial decoder's prefix
+    assert B.lzs_decompress(comp[:len(comp) // 2], len(big)) == (helpers.reference() or helpers.oracle()).decompress(comp[:len(comp) // 2], len(big))

@@ -2,6 +2,8 @@
 against the oracle.  Whatever the piece size and wherever the pieces' borders fall -- inside
 literal runs, inside short matches, inside matches thousands of bytes long -- the stitched stream
 must be the one stream the reference produces (c/src/liblzs/lzs-compression.c:249-467)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -69,3 +71,64 @@ def test_pieces_table_too_small_produces_nothing():
     data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 3000, first_index=1).tobytes()]
     got, _ = emu.compress_pieces(data, 100, cap_entries=10)
     assert got is None
+
+
+# ---------------------------------------------------------------- the decoder for long streams (csrc/k4_pieces.cuh)
+
+def _decode_check(streams, caps, piece, **kw):
+    """Outputs and stop reasons must be the oracle's (= the reference's, tests/test_oracle.py) whether a
+    stream is finished by the piece passes or handed to k4_decode as dirty."""
+    o = helpers.oracle()
+    got, stats, status = emu.decode_pieces(streams, caps, piece, with_status=True, **kw)
+    for i, (s, c, g) in enumerate(zip(streams, caps, got)):
+        want, why = o.decompress_status(s, c)
+        assert g == want, "stream %d, piece %d" % (i, piece)
+        assert int(status[i]) == why, "status of stream %d, piece %d: %d, want %d" % (i, piece, int(status[i]), why)
+    return stats
+
+
+@pytest.mark.parametrize("piece", [16, 50, 333])
+def test_decode_pieces_clean_streams(piece):
+    o = helpers.oracle()
+    cases = helpers.edge_case_inputs()
+    data = [cases[k] for k in cases if len(cases[k]) <= 6000]
+    data += [helpers.corpus(kind, 1, 4000, first_index=4).tobytes()
+             for kind in (helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_RANDOM, helpers.CORPUS_PACKET)]
+    comp = [o.compress(d) for d in data]
+    for slack in (0, 1, 100):                   # a full output stops the decoder before the end marker: another status
+        stats = _decode_check(comp, [len(d) + slack for d in data], piece)
+        assert stats[1] == 0 and stats[3] == 0  # nothing left to k4_decode
+
+
+def test_decode_pieces_long_tokens_and_unaligned():
+    """Matches whose continuation nibbles run through many pieces (runs), streams and outputs at odd
+    addresses."""
+    o = helpers.oracle()
+    rng = np.random.default_rng(3)
+    noise = lambda n: rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    data = [noise(50) + b"\0" * 60000 + noise(30), b"ab" * 20000, noise(20) + b"z" * 2100 + noise(5) + b"y" * 2046 + b"x" * 2048]
+    comp = [o.compress(d) for d in data]
+    for lead, out_lead in ((0, 0), (1, 3), (3, 5)):
+        stats = _decode_check(comp, [len(d) + 3 for d in data], 16, align=4, lead=lead, out_lead=out_lead)
+        assert stats[1] == 0
+
+
+def test_decode_pieces_damaged_streams_and_short_outputs():
+    """Everything that is not a clean stream is k4_decode's: the committed outputs of the unmodified
+    reference on damaged streams and short capacities, random bit strings, a table that is too small."""
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "ref_cases.npz"))
+    keys = [k for k in z.files if k.startswith("dec_in__")]
+    streams = [z[k].tobytes() for k in keys]
+    caps = [int(k.split("__")[2]) for k in keys]
+    want = [z["dec_out__" + k[len("dec_in__"):]].tobytes() for k in keys]
+    got, stats = emu.decode_pieces(streams, caps, 24)
+    assert got == want
+    assert stats[1] > 0
+    rng = np.random.default_rng(5)
+    streams = [rng.integers(0, 256, int(rng.integers(0, 400)), dtype=np.uint8).tobytes() for _ in range(60)]
+    caps = [int(rng.integers(0, 3000)) for _ in streams]
+    _decode_check(streams, caps, 32)
+    o = helpers.oracle()
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 3000, first_index=i).tobytes() for i in range(3)]
+    stats = _decode_check([o.compress(d) for d in data], [len(d) for d in data], 64, cap_entries=5)
+    assert stats[3] == 1 and stats[1] == 3

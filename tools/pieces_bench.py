@@ -64,6 +64,36 @@ def main():
         print(json.dumps(row), flush=True)
     B.set_piece_bytes(65536)
 
+    # the decoder: pieces of the compressed stream (csrc/k4_pieces.cuh) against one group of lanes per stream
+    for kib in ((1024,) if quick else (64, 128, 256, 512, 1024, 16384, 262144)):
+        chunk = kib << 10
+        row = {"decode_chunk_kib": kib, "streams": total // chunk}
+        db = B.DeviceBatch(total, chunk)
+        B.check(B.lib().lzs_b200_corpus_fill_device(db.raw.data_ptr(), 65536, 65536, 0, total // 65536, 0x5EED0002,
+                                                    B.CORPUS_MIXED, db._stream()))
+        db.compress()
+        torch.cuda.synchronize()
+        for dpiece in (0, 2048, 4096):
+            if dpiece == 0 and total // chunk < 64:
+                continue                      # one group of lanes per stream: minutes
+            B.set_decode_piece_bytes(dpiece)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            best = 1e30
+            before = B.lib().lzs_b200_kernel_launches()
+            iters = 1 if dpiece == 0 and total // chunk < 1024 else 3
+            for _ in range(iters):
+                db.dec.zero_()
+                ev[0].record(); db.decompress(); ev[1].record()
+                torch.cuda.synchronize()
+                best = min(best, ev[0].elapsed_time(ev[1]))
+            cut = (B.lib().lzs_b200_kernel_launches() - before) // iters == 9
+            assert db.roundtrip_ok(), "decode differs with pieces of %d" % dpiece
+            row["dpiece_%d" % dpiece if dpiece else "uncut"] = {"ms": round(best, 2), "gbs": round(total / best / 1e6, 2), "cut": cut}
+        B.set_decode_piece_bytes(2048)
+        del db
+        torch.cuda.empty_cache()
+        print(json.dumps(row), flush=True)
+
     # the drop-in call on one large host buffer
     ref = helpers.reference() or helpers.oracle()
     for mib in (1, 16, 256):
@@ -77,8 +107,16 @@ def main():
             t0 = time.perf_counter(); r = B.lib().lzs_compress(B._p(dst), cap, B._p(src), n); best = min(best, time.perf_counter() - t0)
         t0 = time.perf_counter(); want = ref.compress(data.tobytes()); t_cpu = time.perf_counter() - t0
         assert dst[:r].tobytes() == want
+        comp = np.ascontiguousarray(dst[:r]); back = np.zeros(n + 16, dtype=np.uint8)
+        best_d = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter(); rd = B.lib().lzs_decompress(B._p(back), n, B._p(comp), r); best_d = min(best_d, time.perf_counter() - t0)
+        assert rd == n and back[:n].tobytes() == data.tobytes()
+        t0 = time.perf_counter(); ref.decompress(want, n); t_cpu_d = time.perf_counter() - t0
         print(json.dumps({"single_call_mib": mib, "lzs_compress_ms": round(best * 1e3, 2), "gbs": round(n / best / 1e9, 3),
-                          "reference_one_core_gbs": round(n / t_cpu / 1e9, 3), "host_memory": "pageable"}), flush=True)
+                          "reference_one_core_gbs": round(n / t_cpu / 1e9, 3), "lzs_decompress_ms": round(best_d * 1e3, 2),
+                          "decompress_gbs": round(n / best_d / 1e9, 3), "reference_one_core_decompress_gbs": round(n / t_cpu_d / 1e9, 3),
+                          "host_memory": "pageable"}), flush=True)
 
 
 if __name__ == "__main__":
