@@ -526,173 +526,235 @@ k4p_emit(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, co
 
 /* ---------------------------------------------------------------- copy */
 
-/* One warp per stream replays the match records in order -- the serial step that is left.  The warp
- * keeps the last 4 KiB of the output in shared memory: bytes enter it from the output slot (where
- * emit has put the literals), matches are copied inside it, finished bytes go back to the slot.
+/* One block per stream replays the match records in order -- the serial step that is left.  The
+ * block keeps the last 4 KiB of the output in shared memory: bytes enter it from the output slot
+ * (where emit has put the literals), matches are copied inside it, finished bytes go back to the slot.
  *   Byte k of a match is byte (k mod offset) behind pos - offset, all of which exist before the match
- * starts, so a match depends on earlier matches only through its source bytes.  32 records are
- * taken at a time, one per lane; a lane copies its match as soon as everything in front of its
- * source range is final -- most sources lie before the 32 records altogether, so a few rounds do
- * what 32 dependent steps would.  Records that are long (or carry many literals) are taken by the
- * whole warp in turn; a match that does not fit the window is copied in the slot itself. */
+ * starts, so a match depends on earlier matches only through its source bytes.  128 records are
+ * taken at a time, one per thread; a scan of literals + lengths gives every match its place, and a
+ * thread copies its match as soon as everything in front of its source range is final -- most
+ * sources lie before the 128 records altogether, so a few rounds do what 128 dependent steps
+ * would.  Matches longer than 16 bytes are copied by the 32 lanes of their thread's warp; a record
+ * that does not fit the window (2 KiB ahead) is copied in the slot itself by the whole block. */
 constexpr uint32_t kDRing = 4096, kDRingAhead = 2048;
-constexpr uint32_t kDLaneLen = 16;                      /* matches up to this long are copied by one lane */
-constexpr uint32_t kDLaneSpan = 64;                     /* literals + length a lane's record may cover: 32 of them fit the window */
+constexpr uint32_t kDLaneLen = 16;                      /* matches up to this long are copied by one thread */
+constexpr int      kDCopyThreads = 128;
 
-/* bytes [flushed, upto) leave the ring, bytes [loaded, ...) enter it as far as the window allows
- * (one copy of this code: it is called from six places) */
+/* bytes [flushed, upto) leave the ring, bytes [loaded, ...) enter it as far as the window allows; whole block */
 __device__ __noinline__ void dring_refill(uint8_t *ring, uint8_t *dst, uint32_t total, uint32_t upto, uint32_t &flushed,
                                           uint32_t &loaded)
 {
-    const uint32_t lane = lane_id();
-    constexpr uint32_t kMask = kDRing - 1u;
-    for (uint32_t p = flushed + lane; p < upto; p += 32u) dst[p] = ring[p & kMask];
+    constexpr uint32_t kMask = kDRing - 1u, kT = kDCopyThreads;
+    for (uint32_t p = flushed + threadIdx.x; p < upto; p += kT) dst[p] = ring[p & kMask];
     flushed = upto;
-    __syncwarp();
+    __syncthreads();
     const uint32_t want = umin32(total, upto + kDRingAhead);
-    uint32_t       p = loaded + lane;
-    for (; p + 224u < want; p += 256u) {                 /* eight loads in flight per lane */
+    uint32_t       p = loaded + threadIdx.x;
+    for (; p + 7u * kT < want; p += 8u * kT) {           /* eight loads in flight per thread */
         uint8_t b[8];
 #pragma unroll
-        for (uint32_t j = 0; j < 8u; j++) b[j] = dst[p + 32u * j];
+        for (uint32_t j = 0; j < 8u; j++) b[j] = dst[p + kT * j];
 #pragma unroll
-        for (uint32_t j = 0; j < 8u; j++) ring[(p + 32u * j) & kMask] = b[j];
+        for (uint32_t j = 0; j < 8u; j++) ring[(p + kT * j) & kMask] = b[j];
     }
-    for (; p < want; p += 32u) ring[p & kMask] = dst[p];
+    for (; p < want; p += kT) ring[p & kMask] = dst[p];
     if (want > loaded) loaded = want;
-    __syncwarp();
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kDCopyThreads)
 k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_len, uint32_t n_streams,
          DPieceTable t)
 {
-    __shared__ uint8_t s_ring[4][kDRing];
-    const uint32_t sid = blockIdx.x * 4u + (threadIdx.x >> 5);
+    __shared__ uint8_t  ring[kDRing];
+    __shared__ uint32_t s_start[kDCopyThreads];          /* where every thread's match starts */
+    __shared__ uint32_t s_mend[kDCopyThreads];           /* and ends */
+    __shared__ uint32_t s_w[2][4];                       /* per-warp words of the block-wide steps */
+    __shared__ uint32_t s_any;
+    const uint32_t sid = blockIdx.x;
     if (sid >= n_streams || t.count[1] || t.dirty[sid]) return;
-    const uint32_t lane = lane_id();
-    uint8_t       *ring = s_ring[threadIdx.x >> 5];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint8_t       *dst = out + out_off[sid];
     const uint32_t total = out_len[sid];                 /* the sweep's */
     const uint32_t first = t.first[sid], np = t.first[sid + 1] - first;
-    constexpr uint32_t kMask = kDRing - 1u;
-    uint32_t       pos = 0, flushed = 0, loaded = 0;     /* output bytes done / written back / present in the ring */
+    constexpr uint32_t kMask = kDRing - 1u, kT = kDCopyThreads;
+    uint32_t       pos = 0, flushed = 0, loaded = 0;     /* output bytes done / written back / present in the ring; the same in every thread */
     bool           before_start = false;
 
-    auto refill = [&](uint32_t upto) { dring_refill(ring, dst, total, upto, flushed, loaded); };
-    refill(0);
+    /* sum over the warps before mine, and over all, of one word per warp */
+    auto across_warps = [&](uint32_t mine_total, uint32_t &before, uint32_t &all, int buf) {
+        if (lane == 0) s_w[buf][warp] = mine_total;
+        __syncthreads();
+        before = 0;
+        all = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 4u; w++) {
+            const uint32_t x = s_w[buf][w];
+            if (w < warp) before += x;
+            all += x;
+        }
+    };
+
+    dring_refill(ring, dst, total, 0u, flushed, loaded);
     for (uint32_t k = 0; k < np && !before_start; k++) {
         const uint32_t idx = first + k;
         const uint32_t nrec = t.nrec[idx];
         if (nrec == 0u) continue;
         const uint32_t *rec = t.records + static_cast<size_t>(idx) * t.stride;
         const uint32_t *longs = t.longs + static_cast<size_t>(idx) * t.lstride;
-        uint32_t        nlong = 0;
-        uint32_t        v_next = lane < nrec ? rec[lane] : 0u;
-        for (uint32_t r0 = 0; r0 < nrec && !before_start; r0 += 32u) {
-            const uint32_t cnt = umin32(32u, nrec - r0);
-            const bool     valid = lane < cnt;
-            const uint32_t v = v_next;
-            v_next = r0 + 32u + lane < nrec ? rec[r0 + 32u + lane] : 0u;   /* the next 32, while these are replayed */
+        uint32_t        nlong = 0, r0 = 0;
+        while (r0 < nrec) {
+            const bool     have = r0 + tid < nrec;
+            const uint32_t v = have ? rec[r0 + tid] : 0u;
             const uint32_t off = v & 0x7FFu, lits = v >> 22;
             uint32_t       len = (v >> 11) & 0x7FFu;
+            const bool     is_long = have && len == 0u && off != 0u;
             {
-                const bool     is_long = valid && len == 0u && off != 0u;
                 const uint32_t lm = __ballot_sync(LZS_FULL_MASK, is_long);
-                if (is_long) len = longs[nlong + static_cast<uint32_t>(__popc(lm & ((1u << lane) - 1u)))];
-                nlong += static_cast<uint32_t>(__popc(lm));
+                uint32_t       before, all;
+                across_warps(static_cast<uint32_t>(__popc(lm)), before, all, 0);
+                if (is_long) len = longs[nlong + before + static_cast<uint32_t>(__popc(lm & ((1u << lane) - 1u)))];
             }
-            /* where every record's match starts: a scan of literals + lengths */
-            uint32_t incl = lits + len;
+            /* where every record's match starts: a scan of literals + lengths over the block */
+            uint32_t incl = have ? lits + len : 0u;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t u = __shfl_up_sync(LZS_FULL_MASK, incl, static_cast<unsigned>(d));
                 if (lane >= static_cast<uint32_t>(d)) incl += u;
             }
+            {
+                uint32_t before, all;
+                across_warps(__shfl_sync(LZS_FULL_MASK, incl, 31), before, all, 1);
+                incl += before;
+            }
+            /* records are taken while they fit the window; the first one always is */
+            const bool     fits = have && (incl <= kDRingAhead || tid == 0u);
+            uint32_t       nb;
+            {
+                const uint32_t fm = __ballot_sync(LZS_FULL_MASK, fits);
+                /* fits is a prefix property (incl grows): count the leading ones over the block */
+                uint32_t before, all;
+                across_warps(static_cast<uint32_t>(__popc(fm)), before, all, 0);
+                nb = all;
+            }
+            const bool     valid = tid < nb;
+            {
+                /* long lengths consumed by the records taken */
+                const uint32_t lm = __ballot_sync(LZS_FULL_MASK, is_long && valid);
+                uint32_t       before, all;
+                across_warps(static_cast<uint32_t>(__popc(lm)), before, all, 1);
+                nlong += all;
+            }
             const uint32_t mstart = pos + incl - len;    /* first byte of my match */
-            const uint32_t batch_end = pos + __shfl_sync(LZS_FULL_MASK, incl, 31);
-            if (__any_sync(LZS_FULL_MASK, valid && len != 0u && off > mstart)) {
-                before_start = true;                     /* reaches before the output: the reference has a rule, k4_decode knows it */
+            if (tid == nb - 1u) s_any = pos + incl;      /* where the batch ends */
+            /* an offset that reaches before the output: the reference has a rule, k4_decode knows it */
+            if (__syncthreads_or(valid && len != 0u && off > mstart)) {
+                before_start = true;
                 break;
             }
-            const bool     big = valid && (len > kDLaneLen || lits + len > kDLaneSpan);
-            const uint32_t bigmask = __ballot_sync(LZS_FULL_MASK, big);
-            const uint32_t src_end = mstart - off + umin32(len, off);
-            uint32_t       cur = 0;
-            while (cur < cnt) {
-                const uint32_t bm = bigmask & ~((1u << cur) - 1u);
-                const uint32_t fb = bm ? static_cast<uint32_t>(__ffs(static_cast<int>(bm)) - 1) : cnt;
-                if (fb > cur) {
-                    /* records [cur, fb): one lane each */
-                    const uint32_t seg_pos = __shfl_sync(LZS_FULL_MASK, mstart - lits, static_cast<int>(cur));
-                    const uint32_t seg_end = __shfl_sync(LZS_FULL_MASK, mstart + len, static_cast<int>(fb - 1u));
-                    if (seg_end > loaded) refill(seg_pos);
-                    const bool in_seg = lane >= cur && lane < fb;
-                    bool       done = !in_seg || len == 0u;
-                    for (;;) {
-                        const uint32_t dm = __ballot_sync(LZS_FULL_MASK, done);
-                        if (dm == LZS_FULL_MASK) break;
-                        const uint32_t head = static_cast<uint32_t>(__ffs(static_cast<int>(~dm)) - 1);
-                        const uint32_t final_to = __shfl_sync(LZS_FULL_MASK, mstart, static_cast<int>(head));
-                        if (!done && (lane == head || src_end <= final_to)) {
-                            /* all source bytes lie before the match, so reads and writes of different
-                             * bytes never meet: four at a time, the offset's period kept by a counter */
-                            const uint32_t from0 = mstart - off;
-                            uint32_t       f = 0;
-                            for (uint32_t i0 = 0; i0 < len; i0 += 4u) {
-                                uint8_t b[4];
+            const uint32_t batch_end = s_any;
+            s_start[tid] = valid ? mstart : 0xFFFFFFFFu;
+            s_mend[tid] = valid ? mstart + len : 0xFFFFFFFFu;
+            if (batch_end > loaded) dring_refill(ring, dst, total, pos, flushed, loaded);
+            else __syncthreads();
+            if (batch_end > loaded) {
+                /* one record that does not fit the window: in the slot itself, by the whole block
+                 * (everything before it is in the slot after the refill) */
+                const uint32_t m0 = s_start[0];
+                const uint32_t b_len = batch_end - m0;
+                const uint32_t b_off = rec[r0] & 0x7FFu;
+                const uint8_t *src = dst + m0 - b_off;
+                for (uint32_t i = tid; i < b_len; i += kT) dst[m0 + i] = src[i < b_off ? i : i % b_off];
+                __syncthreads();
+                flushed = batch_end;                     /* the window starts again behind the match */
+                loaded = batch_end > kWindow ? batch_end - kWindow : 0u;
+                for (uint32_t p = loaded + tid; p < batch_end; p += kT) ring[p & kMask] = dst[p];
+                loaded = batch_end;
+                __syncthreads();
+                dring_refill(ring, dst, total, batch_end, flushed, loaded);
+            } else {
+                /* The matches my source bytes come from: records [qa, qb) of this batch (matches lie in
+                 * the order of their records, so both ends are found by bisection); bytes before the
+                 * batch, and literals, are final already. */
+                const uint32_t src_lo = mstart - off, src_end = src_lo + umin32(len, off);
+                bool           done = !valid || len == 0u;
+                uint32_t       qa = 0, qb = 0;
+                if (!done && src_end > pos) {
+                    uint32_t lo = 0, hi = tid;               /* first record whose match ends behind src_lo */
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (s_mend[mid] > src_lo) hi = mid; else lo = mid + 1u;
+                    }
+                    qa = lo;
+                    lo = qa;
+                    hi = tid;                                /* first record whose match starts at or behind src_end */
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (s_start[mid] >= src_end) hi = mid; else lo = mid + 1u;
+                    }
+                    qb = lo;
+                }
+                uint32_t dep[4];                         /* the same as bits of the four warps' done words */
 #pragma unroll
-                                for (uint32_t j = 0; j < 4u; j++) {
-                                    b[j] = ring[(from0 + f) & kMask];
-                                    f = f + 1u == off ? 0u : f + 1u;
-                                }
+                for (uint32_t w = 0; w < 4u; w++) {
+                    const uint32_t a = qa > w * 32u ? qa - w * 32u : 0u;
+                    const uint32_t b = qb < w * 32u + 32u ? (qb > w * 32u ? qb - w * 32u : 0u) : 32u;
+                    dep[w] = a < b ? (b == 32u ? 0xFFFFFFFFu : (1u << b) - 1u) & ~((1u << a) - 1u) : 0u;
+                }
+                /* one barrier per round: the done words alternate between two buffers, and the ring
+                 * bytes a round writes are read after the next round's barrier at the earliest */
+                for (int buf = 0;; buf ^= 1) {
+                    const uint32_t dm = __ballot_sync(LZS_FULL_MASK, done);
+                    if (lane == 0) s_w[buf][warp] = dm;
+                    __syncthreads();
+                    const uint32_t u0 = ~s_w[buf][0], u1 = ~s_w[buf][1], u2 = ~s_w[buf][2], u3 = ~s_w[buf][3];
+                    if ((u0 | u1 | u2 | u3) == 0u) break;
+                    const bool blocked = ((u0 & dep[0]) | (u1 & dep[1]) | (u2 & dep[2]) | (u3 & dep[3])) != 0u;
+                    const bool     ready = !done && !blocked;
+                    const uint32_t from0 = src_lo;
+                    if (ready && len <= kDLaneLen) {
+                        /* all source bytes lie before the match, so reads and writes of different
+                         * bytes never meet: four at a time, the offset's period kept by a counter */
+                        uint32_t f = 0;
+                        for (uint32_t i0 = 0; i0 < len; i0 += 4u) {
+                            uint8_t b[4];
 #pragma unroll
-                                for (uint32_t j = 0; j < 4u; j++)
-                                    if (i0 + j < len) ring[(mstart + i0 + j) & kMask] = b[j];
+                            for (uint32_t j = 0; j < 4u; j++) {
+                                b[j] = ring[(from0 + f) & kMask];
+                                f = f + 1u == off ? 0u : f + 1u;
                             }
-                            done = true;
+#pragma unroll
+                            for (uint32_t j = 0; j < 4u; j++)
+                                if (i0 + j < len) ring[(mstart + i0 + j) & kMask] = b[j];
                         }
-                        __syncwarp();
                     }
-                }
-                if (fb < cnt) {
-                    /* record fb: the whole warp */
-                    const uint32_t b_lits = __shfl_sync(LZS_FULL_MASK, lits, static_cast<int>(fb));
-                    const uint32_t b_len = __shfl_sync(LZS_FULL_MASK, len, static_cast<int>(fb));
-                    const uint32_t b_off = __shfl_sync(LZS_FULL_MASK, off, static_cast<int>(fb));
-                    const uint32_t b_pos = __shfl_sync(LZS_FULL_MASK, mstart, static_cast<int>(fb));
-                    if (b_pos + b_len > loaded) refill(b_pos - b_lits);
-                    if (b_len != 0u && b_pos + b_len <= loaded) {
-                        const uint32_t from0 = b_pos - b_off;
+                    /* the longer ones of this round: the 32 lanes of the warp, one match after the other */
+                    uint32_t bm = __ballot_sync(LZS_FULL_MASK, ready && len > kDLaneLen);
+                    while (bm) {
+                        const int      l = __ffs(static_cast<int>(bm)) - 1;
+                        const uint32_t b_pos = __shfl_sync(LZS_FULL_MASK, mstart, l);
+                        const uint32_t b_len = __shfl_sync(LZS_FULL_MASK, len, l);
+                        const uint32_t b_off = __shfl_sync(LZS_FULL_MASK, off, l);
+                        const uint32_t b_from = b_pos - b_off;
                         if (b_off >= b_len) {
-                            for (uint32_t i = lane; i < b_len; i += 32u) ring[(b_pos + i) & kMask] = ring[(from0 + i) & kMask];
+                            for (uint32_t i = lane; i < b_len; i += 32u) ring[(b_pos + i) & kMask] = ring[(b_from + i) & kMask];
                         } else {
-                            for (uint32_t i = lane; i < b_len; i += 32u) ring[(b_pos + i) & kMask] = ring[(from0 + i % b_off) & kMask];
+                            for (uint32_t i = lane; i < b_len; i += 32u) ring[(b_pos + i) & kMask] = ring[(b_from + i % b_off) & kMask];
                         }
-                        __syncwarp();
-                    } else if (b_len != 0u) {
-                        /* longer than the window: in the slot itself (everything before it is there after a refill) */
-                        refill(b_pos);
-                        const uint8_t *src = dst + b_pos - b_off;
-                        for (uint32_t i = lane; i < b_len; i += 32u) dst[b_pos + i] = src[i < b_off ? i : i % b_off];
-                        __syncwarp();
-                        const uint32_t e = b_pos + b_len;   /* the window starts again behind the match */
-                        flushed = e;
-                        loaded = e > kWindow ? e - kWindow : 0u;
-                        for (uint32_t p = loaded + lane; p < e; p += 32u) ring[p & kMask] = dst[p];
-                        loaded = e;
-                        __syncwarp();
-                        refill(e);
+                        bm &= bm - 1u;
                     }
+                    done = done || ready;
                 }
-                cur = fb + 1u;
+                __syncthreads();                         /* nobody still reads this batch's words when the next one writes them */
             }
             pos = batch_end;
+            r0 += nb;
         }
     }
+    __syncthreads();
     if (!before_start) {
-        for (uint32_t p = flushed + lane; p < pos; p += 32u) dst[p] = ring[p & kMask];
-    } else if (lane == 0) {
+        for (uint32_t p = flushed + tid; p < pos; p += kT) dst[p] = ring[p & kMask];
+    } else if (tid == 0) {
         t.dirty[sid] = 1;
     }
 }

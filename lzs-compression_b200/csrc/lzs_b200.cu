@@ -449,7 +449,7 @@ int decompress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t 
     lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 1u, t);
     lzs::k4p_sweep<<<sgrid, 128, 0, st>>>(in, in_off, in_len, out_cap, out_len, status, n_streams, piece, t);
     lzs::k4p_emit<<<pgrid, 128, 0, st>>>(in, in_off, in_len, out, out_off, n_streams, piece, t);
-    lzs::k4p_copy<<<sgrid, 128, 0, st>>>(out, out_off, out_len, n_streams, t);
+    lzs::k4p_copy<<<n_streams, lzs::kDCopyThreads, 0, st>>>(out, out_off, out_len, n_streams, t);
     lzs::k4p_dirty_list<<<(n_streams + 127u) / 128u, 128, 0, st>>>(n_streams, t);
     g_launches += 8;
     CUDA_TRY(cudaGetLastError());

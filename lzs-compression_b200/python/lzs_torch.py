@@ -58,9 +58,10 @@ def decompress(comp, comp_off, comp_len, out_off, out_cap, with_status=False):
     out = torch.empty(span + 64, dtype=torch.uint8, device=comp.device)
     out_len = torch.zeros(max(n, 1), dtype=torch.int32, device=comp.device)
     status = torch.zeros(max(n, 1), dtype=torch.uint8, device=comp.device)
-    L.lzs_b200_decompress_scratch_bytes_for.restype = __import__("ctypes").c_size_t
-    L.lzs_b200_decompress_scratch_bytes_for.argtypes = [__import__("ctypes").c_uint32]
-    scratch = torch.empty(L.lzs_b200_decompress_scratch_bytes_for(n), dtype=torch.uint8, device=comp.device)
+    # with room for the piece table of a batch of few long streams (csrc/k4_pieces.cuh); for many
+    # streams this is the launch-order scratch of lzs_b200_decompress_scratch_bytes_for
+    scratch = torch.empty(L.lzs_b200_decompress_scratch_bytes_long(int(comp.numel()), n), dtype=torch.uint8,
+                          device=comp.device)
     _B.check(L.lzs_b200_decompress_status_batch_device(
         comp.data_ptr(), comp_off.data_ptr(), comp_len.data_ptr(), out.data_ptr(), out_off.data_ptr(),
         out_cap.data_ptr(), out_len.data_ptr(), status.data_ptr() if with_status else None, n, scratch.data_ptr(),

@@ -137,7 +137,7 @@ extern "C" int emu_decode_pieces(const uint8_t *in, const uint64_t *in_off, cons
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 1u, t); });
     simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_sweep(in, in_off, in_len, out_cap, out_len, status, n, piece, t); });
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_emit(in, in_off, in_len, out, out_off, n, piece, t); });
-    simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_copy(out, out_off, out_len, n, t); });
+    simt::launch(dim3(n), dim3(lzs::kDCopyThreads), 0, [&] { lzs::k4p_copy(out, out_off, out_len, n, t); });
     simt::launch(dim3((n + 127) / 128), dim3(128), 0, [&] { lzs::k4p_dirty_list(n, t); });
     simt::launch(dim3(2), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<8>(), [&] {
         lzs::k4_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &t.count[3], status, t.dirty_list, nullptr,

@@ -76,6 +76,8 @@ struct Block {
     unsigned  nthreads = 0;
     unsigned  bar_arrived = 0;
     uint64_t  bar_round = 0;
+    int       bar_or_acc = 0;          /* __syncthreads_or: predicate seen in this round / result of the last two rounds */
+    int       bar_or_result[2] = {0, 0};
     std::map<int, std::pair<unsigned, uint64_t>> named;   /* id -> (arrived, round) */
 #ifdef LZS_SIMT_FAST_SWITCH
     void      *sched_sp = nullptr;
@@ -164,6 +166,23 @@ static inline void __syncthreads()
     } else {
         while (b->bar_round == my) simt::yield();
     }
+}
+
+/* barrier that also returns whether the predicate held in any thread of the block */
+static inline int __syncthreads_or(int pred)
+{
+    simt::Block *b = simt::g_block;
+    if (pred) b->bar_or_acc = 1;
+    uint64_t my = b->bar_round;
+    if (++b->bar_arrived == b->nthreads) {
+        b->bar_or_result[my & 1] = b->bar_or_acc;
+        b->bar_or_acc = 0;
+        b->bar_arrived = 0;
+        b->bar_round++;
+    } else {
+        while (b->bar_round == my) simt::yield();
+    }
+    return b->bar_or_result[my & 1];
 }
 
 /* bar.sync id, nthreads (named barrier; every participant calls sync) */

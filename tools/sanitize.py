@@ -78,3 +78,12 @@ B.set_piece_bytes(65536)
 assert got == [o.compress(d) for d in long_data]
 assert cut == [o.compress(long_data[0])[:777], b""]
 print("sanitize workload (pieces) ok")
+# the decoder for long streams (csrc/k4_pieces.cuh): plan, spec, fix x2, sweep, emit, copy, dirty list, k4_decode for the dirty
+B.set_decode_piece_bytes(64)
+comp_long = [o.compress(d) for d in long_data]
+mixed_bag = comp_long + [c[:len(c) // 2] for c in comp_long[:2]] + [bytes(rng.integers(0, 256, 500, dtype=np.uint8)) for _ in range(5)]
+bag_caps = [len(d) for d in long_data] + [len(d) for d in long_data[:2]] + [3000] * 5
+got = B.decompress_streams(mixed_bag, bag_caps)
+B.set_decode_piece_bytes(2048)
+assert got == [o.decompress(s, c) for s, c in zip(mixed_bag, bag_caps)]
+print("sanitize workload (decoder pieces) ok")
