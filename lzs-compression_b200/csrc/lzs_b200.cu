@@ -595,10 +595,11 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
     const uint32_t dpiece = dpiece_bytes();
     const size_t   fixed = kCounterBytes + order_bytes(n_streams);
     if (dpiece != 0 && hist_len == nullptr && n_streams <= kCutStreamsMaxDecode && scratch_bytes > fixed + 4096) {
-        const size_t   per_piece = 4u * (lzs::kDPieceEntryWords + lzs::dpiece_record_stride(dpiece));
-        const uint64_t fit = (scratch_bytes - fixed - 512) / per_piece;
-        const uint32_t cap = fit > 0x7FFFFFFFull ? 0x7FFFFFFFu : static_cast<uint32_t>(fit);
-        if (cap >= 2u * n_streams + 16u)
+        /* as many table entries as the scratch holds (dpiece_table_bytes is linear in them) */
+        const size_t   per_piece = lzs::dpiece_table_bytes(1, dpiece) - lzs::dpiece_table_bytes(0, dpiece);
+        const uint64_t fit = (scratch_bytes - fixed - lzs::dpiece_table_bytes(0, dpiece)) / per_piece;
+        const uint32_t cap = fit > 0x00FFFFFFull ? 0x00FFFFFFu : static_cast<uint32_t>(fit);
+        if (cap >= 2u * n_streams + 16u && fixed + lzs::dpiece_table_bytes(cap, dpiece) <= scratch_bytes)
             return decompress_pieces(in, in_off, in_len, out, out_off, out_cap, out_len, status, n_streams, dpiece, cap,
                                      static_cast<uint8_t *>(scratch) + fixed, st, d);
     }

@@ -23,3 +23,9 @@ timeout 400 python tools/pieces_bench.py > gpurun_out/${R}_pieces_bench.jsonl 2>
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${R}_pieces_launches.csv \
     python tools/prof.py --mib 1024 --chunk 1048576 --iters 2 --compress-only > /dev/null 2>&1
 timeout 200 python tools/zeros_probe.py 2>&1 | tail -2
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${R}_decode_pieces_launches.csv \
+    python tools/decode_prof.py --mib 1024 --chunk 1048576 --iters 1 > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k4p_copy -c 1 -f -o gpurun_out/${R}_k4p_copy \
+    python tools/decode_prof.py --mib 256 --chunk 1048576 --iters 1 > /dev/null 2>&1
+timeout 600 compute-sanitizer --tool memcheck python tools/sanitize.py 2>&1 | tail -7 > gpurun_out/${R}_memcheck.txt; tail -3 gpurun_out/${R}_memcheck.txt
+timeout 600 compute-sanitizer --tool synccheck python tools/sanitize.py 2>&1 | tail -3 > gpurun_out/${R}_synccheck.txt; tail -2 gpurun_out/${R}_synccheck.txt
