@@ -720,7 +720,8 @@ k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__r
                             uint8_t b[4];
 #pragma unroll
                             for (uint32_t j = 0; j < 4u; j++) {
-                                b[j] = ring[(from0 + f) & kMask];
+                                /* no byte behind the source range is touched: another thread may be writing it */
+                                b[j] = i0 + j < len ? ring[(from0 + f) & kMask] : static_cast<uint8_t>(0);
                                 f = f + 1u == off ? 0u : f + 1u;
                             }
 #pragma unroll
