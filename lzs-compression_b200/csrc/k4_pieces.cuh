@@ -538,7 +538,13 @@ k4p_emit(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, co
  * that does not fit the window (2 KiB ahead) is copied in the slot itself by the whole block. */
 constexpr uint32_t kDRing = 4096, kDRingAhead = 2048;
 constexpr uint32_t kDLaneLen = 16;                      /* matches up to this long are copied by one thread */
-constexpr int      kDCopyThreads = 128;
+#ifndef LZS_K4P_COPY_THREADS
+#define LZS_K4P_COPY_THREADS 128
+#endif
+constexpr int      kDCopyThreads = LZS_K4P_COPY_THREADS;   /* records replayed together, one per thread (measured: 64 / 128 / 256
+                                                              threads -> 24.1 / 23.8 / 29.2 ms per GiB in 1 MiB chunks, 2.6 / 1.9 / 1.6 s for
+                                                              4 streams of 256 MiB; loading the next records a batch ahead: no change) */
+constexpr uint32_t kDCopyWarps = kDCopyThreads / 32;
 
 /* bytes [flushed, upto) leave the ring, bytes [loaded, ...) enter it as far as the window allows; whole block */
 __device__ __noinline__ void dring_refill(uint8_t *ring, uint8_t *dst, uint32_t total, uint32_t upto, uint32_t &flushed,
@@ -569,7 +575,7 @@ k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__r
     __shared__ uint8_t  ring[kDRing];
     __shared__ uint32_t s_start[kDCopyThreads];          /* where every thread's match starts */
     __shared__ uint32_t s_mend[kDCopyThreads];           /* and ends */
-    __shared__ uint32_t s_w[2][4];                       /* per-warp words of the block-wide steps */
+    __shared__ uint32_t s_w[2][kDCopyWarps];             /* per-warp words of the block-wide steps */
     __shared__ uint32_t s_any;
     const uint32_t sid = blockIdx.x;
     if (sid >= n_streams || t.count[1] || t.dirty[sid]) return;
@@ -588,7 +594,7 @@ k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__r
         before = 0;
         all = 0;
 #pragma unroll
-        for (uint32_t w = 0; w < 4u; w++) {
+        for (uint32_t w = 0; w < kDCopyWarps; w++) {
             const uint32_t x = s_w[buf][w];
             if (w < warp) before += x;
             all += x;
@@ -694,9 +700,9 @@ k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__r
                     }
                     qb = lo;
                 }
-                uint32_t dep[4];                         /* the same as bits of the four warps' done words */
+                uint32_t dep[kDCopyWarps];               /* the same as bits of the warps' done words */
 #pragma unroll
-                for (uint32_t w = 0; w < 4u; w++) {
+                for (uint32_t w = 0; w < kDCopyWarps; w++) {
                     const uint32_t a = qa > w * 32u ? qa - w * 32u : 0u;
                     const uint32_t b = qb < w * 32u + 32u ? (qb > w * 32u ? qb - w * 32u : 0u) : 32u;
                     dep[w] = a < b ? (b == 32u ? 0xFFFFFFFFu : (1u << b) - 1u) & ~((1u << a) - 1u) : 0u;
@@ -707,9 +713,15 @@ k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__r
                     const uint32_t dm = __ballot_sync(LZS_FULL_MASK, done);
                     if (lane == 0) s_w[buf][warp] = dm;
                     __syncthreads();
-                    const uint32_t u0 = ~s_w[buf][0], u1 = ~s_w[buf][1], u2 = ~s_w[buf][2], u3 = ~s_w[buf][3];
-                    if ((u0 | u1 | u2 | u3) == 0u) break;
-                    const bool blocked = ((u0 & dep[0]) | (u1 & dep[1]) | (u2 & dep[2]) | (u3 & dep[3])) != 0u;
+                    uint32_t undone = 0, waits = 0;
+#pragma unroll
+                    for (uint32_t w = 0; w < kDCopyWarps; w++) {
+                        const uint32_t u = ~s_w[buf][w];
+                        undone |= u;
+                        waits |= u & dep[w];
+                    }
+                    if (undone == 0u) break;
+                    const bool blocked = waits != 0u;
                     const bool     ready = !done && !blocked;
                     const uint32_t from0 = src_lo;
                     if (ready && len <= kDLaneLen) {
