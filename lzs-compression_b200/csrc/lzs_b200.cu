@@ -1048,7 +1048,8 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     /* A decoder writes every output byte exactly once and reads none back (its history is in shared
      * memory), so when the caller's output buffer is pinned and device mapped it CAN decode straight
      * into it over PCIe (option, off by default: see mapped_host_range). */
-    uint8_t *const direct_out = decompress ? mapped_host_range(out, out_span) : nullptr;
+    /* (not for the piece decoder: its copy pass reads the output back) */
+    uint8_t *const direct_out = decompress && !long_decode ? mapped_host_range(out, out_span) : nullptr;
     if ((rc = p.reserve(S_IN, in_span + 64))) return rc;
     if (!direct_out && (rc = p.reserve(S_OUT, out_span + 64))) return rc;
     if ((rc = p.reserve(S_INOFF, n * sizeof(uint64_t)))) return rc;
