@@ -537,7 +537,11 @@ k4p_emit(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, co
  * would.  Matches longer than 16 bytes are copied by the 32 lanes of their thread's warp; a record
  * that does not fit the window (2 KiB ahead) is copied in the slot itself by the whole block. */
 constexpr uint32_t kDRing = 4096, kDRingAhead = 2048;
-constexpr uint32_t kDLaneLen = 16;                      /* matches up to this long are copied by one thread */
+#ifndef LZS_K4P_LANE_LEN
+#define LZS_K4P_LANE_LEN 16
+#endif
+constexpr uint32_t kDLaneLen = LZS_K4P_LANE_LEN;        /* matches up to this long are copied by one thread (4 / 8 / 16 / 32: no
+                                                           difference beyond the noise between boxes) */
 #ifndef LZS_K4P_COPY_THREADS
 #define LZS_K4P_COPY_THREADS 128
 #endif
