@@ -132,3 +132,64 @@ def test_decode_pieces_damaged_streams_and_short_outputs():
     data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 3000, first_index=i).tobytes() for i in range(3)]
     stats = _decode_check([o.compress(d) for d in data], [len(d) for d in data], 64, cap_entries=5)
     assert stats[3] == 1 and stats[1] == 3
+
+
+# ---------------------------------------------------------------- structured fuzz, both directions
+
+def _structured(rng, n):
+    """Runs, short periods, copies of earlier bytes, small alphabets, noise, text: what makes piece borders
+    fall into every kind of token."""
+    out = bytearray()
+    while len(out) < n:
+        r = rng.integers(0, 6)
+        if r == 0:
+            out += rng.integers(0, 256, int(rng.integers(1, 60)), dtype=np.uint8).tobytes()
+        elif r == 1:
+            out += bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 4000))
+        elif r == 2:
+            out += rng.integers(0, 4, int(rng.integers(1, 9)), dtype=np.uint8).tobytes() * int(rng.integers(1, 300))
+        elif r == 3 and len(out) > 10:
+            a = int(rng.integers(0, len(out)))
+            out += out[a:a + int(rng.integers(2, 40))]
+        elif r == 4:
+            out += rng.integers(0, 3, int(rng.integers(1, 100)), dtype=np.uint8).tobytes()
+        else:
+            out += b"the quick brown fox "[:int(rng.integers(1, 20))]
+    return bytes(out[:n])
+
+
+def test_pieces_structured_fuzz_compressor():
+    rng = np.random.default_rng(77)
+    for _ in range(8):
+        data = [_structured(rng, int(rng.integers(1, 9000))) for _ in range(4)]
+        _check(data, int(rng.integers(64, 400)), grid=2)
+
+
+def test_pieces_structured_fuzz_decoder():
+    """Clean, truncated, damaged and padded streams with exact, generous and short capacities, at odd
+    addresses: bytes and stop reasons are the oracle's for every piece size."""
+    o = helpers.oracle()
+    rng = np.random.default_rng(78)
+    for _ in range(40):
+        data = [_structured(rng, int(rng.integers(1, 20000))) for _ in range(6)]
+        streams, caps = [], []
+        for d in data:
+            c = o.compress(d)
+            k = int(rng.integers(0, 6))
+            if k == 0:
+                streams.append(c); caps.append(len(d))
+            elif k == 1:
+                streams.append(c); caps.append(len(d) + int(rng.integers(1, 50)))
+            elif k == 2:
+                streams.append(c[:int(rng.integers(0, len(c) + 1))]); caps.append(len(d) + 5)
+            elif k == 3:
+                streams.append(c); caps.append(int(rng.integers(0, len(d) + 1)))
+            elif k == 4:
+                b = bytearray(c)
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+                streams.append(bytes(b)); caps.append(len(d) + int(rng.integers(0, 3000)))
+            else:
+                streams.append(c + rng.integers(0, 256, 7, dtype=np.uint8).tobytes()); caps.append(len(d) + 9)
+        _decode_check(streams, caps, int(rng.integers(16, 300)), lead=int(rng.integers(0, 4)), align=4,
+                      out_lead=int(rng.integers(0, 8)))
