@@ -680,3 +680,37 @@ def test_one_large_buffer_decoded_through_the_drop_in_call(B):
     assert B.lzs_decompress(comp, len(big) + 1000) == big
     assert B.lzs_decompress(comp, 1 << 20) == big[:1 << 20]                      # too small: the serial decoder's prefix
     assert B.lzs_decompress(comp[:len(comp) // 2], len(big)) == (helpers.reference() or helpers.oracle()).decompress(comp[:len(comp) // 2], len(big))
+
+
+def test_long_streams_structured_fuzz_both_directions(B):
+    """Runs, periods, copies, small alphabets, noise and text in 300 streams of 2-40 KB through the piece
+    compressor (pieces of 1 KiB) and the piece decoder (pieces of 64 bytes), clean and damaged, against
+    the unmodified reference."""
+    import test_pieces
+    ref = helpers.reference() or helpers.oracle()
+    rng = np.random.default_rng(91)
+    data = [test_pieces._structured(rng, int(rng.integers(2000, 40000))) for _ in range(300)]
+    want = [ref.compress(d) for d in data]
+    B.set_piece_bytes(1024)
+    B.set_decode_piece_bytes(64)
+    try:
+        got = B.compress_streams(data)
+        assert got == want
+        streams, caps = [], []
+        for i, (c, d) in enumerate(zip(want, data)):
+            k = i % 6
+            if k == 0:   streams.append(c); caps.append(len(d))
+            elif k == 1: streams.append(c); caps.append(len(d) + 33)
+            elif k == 2: streams.append(c[:int(rng.integers(0, len(c) + 1))]); caps.append(len(d) + 5)
+            elif k == 3: streams.append(c); caps.append(int(rng.integers(0, len(d) + 1)))
+            elif k == 4:
+                b = bytearray(c)
+                for _ in range(3): b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+                streams.append(bytes(b)); caps.append(len(d) + 1000)
+            else:        streams.append(c + b"\xff" * 5); caps.append(len(d) + 9)
+        back = B.decompress_streams(streams, caps)
+    finally:
+        B.set_piece_bytes(65536)
+        B.set_decode_piece_bytes(2048)
+    for i, (s, c, g) in enumerate(zip(streams, caps, back)):
+        assert g == ref.decompress(s, c), i
