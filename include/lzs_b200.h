@@ -269,6 +269,21 @@ int lzs_b200_set_piece_bytes(uint32_t bytes);
 size_t lzs_b200_decompress_scratch_bytes_long(uint64_t in_span, uint32_t n_streams);
 int    lzs_b200_set_decode_piece_bytes(uint32_t bytes);
 
+/* A HANDFUL of long streams -- one lzs_decompress call on a large buffer is the case -- cannot keep the
+ * GPU busy even with one thread block replaying each stream's matches (~140 MB/s per stream).  For
+ * them the copies are not replayed at all: every output byte gets a pointer to the byte it is a copy
+ * of, the pointers are doubled until each points at a literal, and every byte is fetched from its
+ * literal (csrc/k4_pieces.cuh: k4j_*).  O(n log n) work and 4 bytes of scratch per byte of out_span,
+ * but parallel over the bytes of a stream: one stream of 256 MiB decodes in 80 ms instead of 1.9 s.
+ * out_span = bytes of `out` the slots cover, at most 2^31.  Same bytes, lengths and stop reasons as
+ * lzs_b200_decompress_status_batch_device (status may be NULL).  lzs_decompress and the host batch call
+ * use it for up to 128 streams (environment: LZS_B200_JUMP_STREAMS, 0 = never). */
+size_t lzs_b200_decompress_scratch_bytes_jump(uint64_t in_span, uint64_t out_span, uint32_t n_streams);
+int    lzs_b200_decompress_long_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                             uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                             uint64_t out_span, uint32_t *out_len, uint8_t *status,
+                                             uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream);
+
 /* Number of kernels launched by this library in the calling process so far. */
 uint64_t lzs_b200_kernel_launches(void);
 

@@ -312,7 +312,8 @@ k4p_spec(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, co
 
 /* pass 0: the entry assumed is the exit of the guess of the piece before.  Where that guess was noise
  * that ended early (it ran into an end-marker pattern before it joined the true orbit) there is
- * nothing to assume yet; pass 1 takes the exit pass 0 found for that piece instead. */
+ * nothing to assume yet, and where it never joined, the assumption is wrong; pass 1 takes the exit
+ * pass 0 found for that piece instead. */
 __global__ void __launch_bounds__(128)
 k4p_fix(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, const uint32_t *__restrict__ in_len,
         uint32_t n_streams, uint32_t piece, uint32_t pass, DPieceTable t)
@@ -323,7 +324,15 @@ k4p_fix(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, con
     const uint32_t k = idx - t.first[sid];
     const uint32_t sraw = t.spec_status[idx];
     uint32_t       fexit = t.spec_exit[idx], fout = t.spec_out[idx], fstatus = sraw & 0xFFu, fentry = kDPieceDead;
-    if (pass != 0u && (k == 0u || t.fix_status[idx] != kDStOpen)) return;
+    /* pass 1 repairs what pass 0 could not know: pieces it left open, and pieces whose assumed entry is
+     * not the exit pass 0 found for the piece before (that piece's guess never joined its true orbit).
+     * Whatever is still wrong afterwards costs the sweep a serial parse of the piece. */
+    if (pass != 0u) {
+        if (k == 0u) return;
+        const bool open = t.fix_status[idx] == kDStOpen;
+        const bool stale = t.fix_status[idx - 1] == kDStOk && t.fix_exit[idx - 1] != t.fix_entry[idx];
+        if (!open && !stale) return;
+    }
     if (k != 0u) {
         const BitSrc   s = bitsrc_open(in + in_off[sid], in_len[sid]);
         const uint32_t pstart = s.first + 8u * k * piece;
@@ -411,6 +420,32 @@ k4p_sweep(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, c
         const uint32_t r_fs = have ? t.fix_status[idx] : 0u;
         const uint32_t r_a = have ? t.fix_entry[idx] : kDPieceDead;   /* the entry fix assumed, if it assumed one */
         uint32_t my_entry = kDPieceDead, my_at = 0;
+        /* The usual case, 32 pieces at once: every piece's assumed entry is the exit fix found for the
+         * piece before it, so all 32 results stand and a scan places them.  (The first and the last
+         * pieces of a stream, and whatever fix left open, take the loop below.) */
+        {
+            uint32_t prev_exit = __shfl_up_sync(LZS_FULL_MASK, r_fx, 1);
+            if (lane == 0) prev_exit = e;
+            const bool chain = !have || (r_fs == kDStOk && r_a == prev_exit);
+            if (!ended && !bad && __all_sync(LZS_FULL_MASK, chain)) {
+                const uint32_t pend = umin32(s.first + 8u * (k0 + lane + 1u) * piece, s.end);
+                uint64_t       incl = have ? r_fo : 0u;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint64_t u = __shfl_up_sync(LZS_FULL_MASK, incl, static_cast<unsigned>(d));
+                    if (lane >= static_cast<uint32_t>(d)) incl += u;
+                }
+                const uint64_t at = pos + incl - (have ? r_fo : 0u);
+                pos += __shfl_sync(LZS_FULL_MASK, incl, 31);
+                e = __shfl_sync(LZS_FULL_MASK, r_fx, static_cast<int>(cnt - 1u));
+                if (pos > cap) bad = true;
+                if (have) {
+                    t.entry[idx] = (bad || prev_exit >= pend) ? kDPieceDead : prev_exit;
+                    t.out_at[idx] = static_cast<uint32_t>(at);
+                }
+                continue;
+            }
+        }
         for (uint32_t k = 0; k < cnt; k++) {
             const uint32_t p0 = s.first + 8u * (k0 + k) * piece;
             const uint32_t pend = umin32(p0 + 8u * piece, s.end);
@@ -773,6 +808,117 @@ k4p_copy(uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__r
         for (uint32_t p = flushed + tid; p < pos; p += kT) dst[p] = ring[p & kMask];
     } else if (tid == 0) {
         t.dirty[sid] = 1;
+    }
+}
+
+/* ---------------------------------------------------------------- few streams: pointer jumping instead of the replay
+ *
+ * The replay above runs at the latency of one thread block per stream (~140 MB/s): fine for hundreds of
+ * streams, hopeless for ONE (a single lzs_decompress call on a large buffer).  For that case the copies
+ * are not replayed at all.  Every output byte gets a pointer to the byte it is a copy of -- itself for
+ * a literal; pos - offset + (k mod offset) for byte k of a match, always an EARLIER byte -- and the
+ * pointers are doubled, S[p] = S[S[p]], until every one of them points at a literal (log2 of the longest
+ * chain of copies rounds; in place, since a pointer only ever moves towards its literal).  Then every
+ * match byte is fetched from its literal.  O(n log n) work and 4 bytes of scratch per output byte,
+ * but all of it parallel over the bytes of the stream.  Positions are offsets from `base` in `out`.
+ */
+constexpr int kJumpRounds = 32;                          /* chains are shorter than 2^32 */
+
+__global__ void k4j_init(uint32_t *__restrict__ S, uint32_t span, uint32_t *__restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= static_cast<uint32_t>(kJumpRounds)) flags[i] = i == 0u ? 1u : 0u;
+    for (uint32_t p = i; p < span; p += gridDim.x * blockDim.x) S[p] = p;
+}
+
+/* One warp per piece: the pointers of its matches (32 records at a time, a scan gives their places;
+ * one lane per match, the long ones by the whole warp). */
+__global__ void __launch_bounds__(128)
+k4j_fill(const uint64_t *__restrict__ out_off, uint64_t base, uint32_t n_streams, uint32_t *__restrict__ S, DPieceTable t)
+{
+    const uint32_t idx = blockIdx.x * 4u + (threadIdx.x >> 5);
+    if (idx >= t.count[0]) return;
+    const uint32_t nrec = t.nrec[idx];
+    if (nrec == 0u) return;
+    const uint32_t lane = lane_id();
+    const uint32_t sid = dpiece_stream(t.first, n_streams, idx);
+    if (t.dirty[sid]) return;
+    const uint32_t o = static_cast<uint32_t>(out_off[sid] - base);
+    const uint32_t *rec = t.records + static_cast<size_t>(idx) * t.stride;
+    const uint32_t *longs = t.longs + static_cast<size_t>(idx) * t.lstride;
+    uint32_t        pos = t.out_at[idx], nlong = 0;
+    bool            before_start = false;
+    for (uint32_t r0 = 0; r0 < nrec; r0 += 32u) {
+        const bool     valid = r0 + lane < nrec;
+        const uint32_t v = valid ? rec[r0 + lane] : 0u;
+        const uint32_t off = v & 0x7FFu, lits = v >> 22;
+        uint32_t       len = (v >> 11) & 0x7FFu;
+        {
+            const bool     is_long = valid && len == 0u && off != 0u;
+            const uint32_t lm = __ballot_sync(LZS_FULL_MASK, is_long);
+            if (is_long) len = longs[nlong + static_cast<uint32_t>(__popc(lm & ((1u << lane) - 1u)))];
+            nlong += static_cast<uint32_t>(__popc(lm));
+        }
+        uint32_t incl = lits + len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(LZS_FULL_MASK, incl, static_cast<unsigned>(d));
+            if (lane >= static_cast<uint32_t>(d)) incl += u;
+        }
+        const uint32_t mstart = pos + incl - len;
+        pos += __shfl_sync(LZS_FULL_MASK, incl, 31);
+        if (__any_sync(LZS_FULL_MASK, valid && len != 0u && off > mstart)) {
+            before_start = true;                         /* k4_decode knows the rule */
+            break;
+        }
+        const uint32_t from0 = o + mstart - off, to0 = o + mstart;
+        if (len <= 32u) {
+            uint32_t f = 0;
+            for (uint32_t i = 0; i < len; i++) {
+                S[to0 + i] = from0 + f;
+                f = f + 1u == off ? 0u : f + 1u;
+            }
+        }
+        uint32_t bm = __ballot_sync(LZS_FULL_MASK, len > 32u);
+        while (bm) {
+            const int      l = __ffs(static_cast<int>(bm)) - 1;
+            const uint32_t b_to = __shfl_sync(LZS_FULL_MASK, to0, l), b_from = __shfl_sync(LZS_FULL_MASK, from0, l);
+            const uint32_t b_len = __shfl_sync(LZS_FULL_MASK, len, l), b_off = __shfl_sync(LZS_FULL_MASK, off, l);
+            if (b_off >= b_len) {
+                for (uint32_t i = lane; i < b_len; i += 32u) S[b_to + i] = b_from + i;
+            } else {
+                for (uint32_t i = lane; i < b_len; i += 32u) S[b_to + i] = b_from + i % b_off;
+            }
+            bm &= bm - 1u;
+        }
+    }
+    if (before_start && lane == 0) t.dirty[sid] = 1;
+}
+
+/* One round of doubling; returns at once when the round before changed nothing. */
+__global__ void k4j_jump(uint32_t *S, uint32_t span, uint32_t *flags, uint32_t round)
+{
+    if (flags[round] == 0u) return;
+    bool changed = false;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < span; p += gridDim.x * blockDim.x) {
+        const uint32_t s = S[p];
+        if (s != p) {
+            const uint32_t s2 = S[s];
+            if (s2 != s) {
+                S[p] = s2;
+                changed = true;
+            }
+        }
+    }
+    if (changed) flags[round + 1u] = 1u;
+}
+
+__global__ void k4j_gather(uint8_t *out, uint64_t base, const uint32_t *__restrict__ S, uint32_t span)
+{
+    uint8_t *o = out + base;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < span; p += gridDim.x * blockDim.x) {
+        const uint32_t s = S[p];
+        if (s != p) o[p] = o[s];
     }
 }
 

@@ -158,6 +158,31 @@ uint32_t dpiece_bytes()
     return static_cast<uint32_t>(v);
 }
 constexpr uint32_t kCutStreamsMaxDecode = 4096;
+/* repair passes of k4p_fix after the first (LZS_B200_FIX_REPAIRS): a piece whose guess never joined its true
+ * orbit gives the NEXT piece a wrong entry, and runs of such pieces are repaired one piece per pass */
+int fix_repairs()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_FIX_REPAIRS");
+        v = e ? atoi(e) : 3;         /* measured on 4 streams of 256 MiB: 1 / 2 / 4 passes leave 631 / 46 / 0 of 361 283 pieces
+                                        with a wrong entry, each of which costs the sweep a serial parse (34 ms / 3 / 1) */
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+/* at most this many long streams are decoded by pointer doubling (host calls; LZS_B200_JUMP_STREAMS, 0 = never) */
+uint32_t jump_streams_max()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_JUMP_STREAMS");
+        v = e ? atoi(e) : 128;       /* measured: doubling beats the replay below ~150 equal streams (1 GiB: 45 ms whatever their number,
+                                        against 7.6 s / streams for the replay) */
+        if (v < 0) v = 0;
+    }
+    return static_cast<uint32_t>(v);
+}
 size_t order_bytes(uint32_t n_streams) { return align_up(static_cast<size_t>(n_streams) * sizeof(uint32_t), 256); }
 
 size_t matches_bytes(uint64_t in_span) { return align_up(static_cast<size_t>(in_span) * sizeof(lzs::match_t) + 64, 256); }
@@ -335,6 +360,12 @@ size_t lzs_b200_decompress_scratch_bytes_long(uint64_t in_span, uint32_t n_strea
     return kCounterBytes + order_bytes(n_streams) + align_up(lzs::dpiece_table_bytes(static_cast<uint32_t>(cap > 0x7FFFFFFFull ? 0x7FFFFFFFull : cap), piece), 256);
 }
 
+/* ... and for the pointers of lzs_b200_decompress_long_batch_device: 4 bytes per byte of out_span more */
+size_t lzs_b200_decompress_scratch_bytes_jump(uint64_t in_span, uint64_t out_span, uint32_t n_streams)
+{
+    return lzs_b200_decompress_scratch_bytes_long(in_span, n_streams) + align_up(static_cast<size_t>(out_span) * 4u, 256) + 4096;
+}
+
 int lzs_b200_set_decode_piece_bytes(uint32_t bytes)
 {
     if (bytes != 0 && (bytes < 16 || bytes > (1u << 24))) return fail(LZS_B200_EINVAL, "piece size must be 0 or 16 .. 2^24");
@@ -439,24 +470,46 @@ int launch_k4(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
  * left (malformed, short of output): a launch that ends at once when there are none. */
 int decompress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                       const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint8_t *status,
-                      uint32_t n_streams, uint32_t piece, uint32_t cap, void *table_mem, cudaStream_t st, DeviceInfo *d)
+                      uint32_t n_streams, uint32_t piece, uint32_t cap, void *table_mem, cudaStream_t st, DeviceInfo *d,
+                      uint32_t *jump_S = nullptr, uint32_t jump_span = 0, uint64_t jump_base = 0)
 {
     const lzs::DPieceTable t = lzs::dpiece_table_at(table_mem, cap, piece);
     const unsigned pgrid = (cap + 127u) / 128u, sgrid = (n_streams + 3u) / 4u;
     lzs::k4p_plan<<<1, 1024, 0, st>>>(in_len, n_streams, piece, t);
     lzs::k4p_spec<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, t);
     lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 0u, t);
-    lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 1u, t);
+    for (int rep = 0; rep < fix_repairs(); rep++) lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 1u, t);
     lzs::k4p_sweep<<<sgrid, 128, 0, st>>>(in, in_off, in_len, out_cap, out_len, status, n_streams, piece, t);
     lzs::k4p_emit<<<pgrid, 128, 0, st>>>(in, in_off, in_len, out, out_off, n_streams, piece, t);
-    lzs::k4p_copy<<<n_streams, lzs::kDCopyThreads, 0, st>>>(out, out_off, out_len, n_streams, t);
+    g_launches += 5 + fix_repairs();
+    if (jump_S != nullptr) {
+        /* a handful of streams: every byte finds the literal it is a copy of by pointer doubling
+         * (k4_pieces.cuh) -- parallel over the bytes of a stream, where the replay is one block per stream */
+        uint32_t      *flags = t.count + 8;
+        const unsigned jgrid = static_cast<unsigned>(d->sms) * 8u;
+        lzs::k4j_init<<<jgrid, 256, 0, st>>>(jump_S, jump_span, flags);
+        lzs::k4j_fill<<<(cap + 3u) / 4u, 128, 0, st>>>(out_off, jump_base, n_streams, jump_S, t);
+        for (int r = 0; r < lzs::kJumpRounds; r++) lzs::k4j_jump<<<jgrid, 256, 0, st>>>(jump_S, jump_span, flags, static_cast<uint32_t>(r));
+        lzs::k4j_gather<<<jgrid, 256, 0, st>>>(out, jump_base, jump_S, jump_span);
+        g_launches += 3 + lzs::kJumpRounds;
+    } else {
+        lzs::k4p_copy<<<n_streams, lzs::kDCopyThreads, 0, st>>>(out, out_off, out_len, n_streams, t);
+        g_launches += 1;
+    }
     lzs::k4p_dirty_list<<<(n_streams + 127u) / 128u, 128, 0, st>>>(n_streams, t);
-    g_launches += 8;
+    g_launches += 1;
     CUDA_TRY(cudaGetLastError());
     return launch_k4(in, in_off, in_len, out, out_off, out_cap, out_len, n_streams, t.count + 3, status, t.dirty_list, nullptr,
                      t.count + 2, n_streams, st, d);
 }
 }  // namespace
+
+namespace {
+int decompress_impl(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                    const uint64_t *out_off, const uint32_t *out_cap, const uint32_t *hist_len, uint32_t *out_len,
+                    uint8_t *status, uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream,
+                    uint32_t jump_span);
+}
 
 extern "C" {
 
@@ -580,6 +633,34 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
                                            const uint32_t *hist_len, uint32_t *out_len, uint8_t *status,
                                            uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream)
 {
+    return decompress_impl(in, in_off, in_len, out, out_off, out_cap, hist_len, out_len, status, n_streams, scratch,
+                           scratch_bytes, stream, 0);
+}
+
+/* A handful of long streams: the copies resolved by pointer doubling (k4_pieces.cuh) -- parallel over the
+ * bytes of a stream.  out_span = bytes of `out` covered by the slots (< 2 GiB); scratch of
+ * lzs_b200_decompress_scratch_bytes_jump(in_span, out_span, n_streams). */
+int lzs_b200_decompress_long_batch_device(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                          uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint64_t out_span,
+                                          uint32_t *out_len, uint8_t *status, uint32_t n_streams, void *scratch,
+                                          size_t scratch_bytes, void *stream)
+{
+    if (out_span == 0 || out_span > (1ull << 31)) return fail(LZS_B200_EINVAL, "out_span must be 1 .. 2^31");
+    return decompress_impl(in, in_off, in_len, out, out_off, out_cap, nullptr, out_len, status, n_streams, scratch,
+                           scratch_bytes, stream, static_cast<uint32_t>(out_span));
+}
+
+}  // extern "C"
+
+namespace {
+/* jump_span != 0 (host path, a handful of long streams): the last 4 * jump_span bytes of scratch hold one
+ * pointer per byte of out[0 .. jump_span), and the copies are resolved by pointer doubling instead of
+ * being replayed (k4_pieces.cuh) */
+int decompress_impl(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
+                    const uint64_t *out_off, const uint32_t *out_cap, const uint32_t *hist_len, uint32_t *out_len,
+                    uint8_t *status, uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream,
+                    uint32_t jump_span)
+{
     if (n_streams == 0) return LZS_B200_OK;
     if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len)
         return fail(LZS_B200_EINVAL, "null pointer");
@@ -594,6 +675,14 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
      * token starts found in parallel inside the streams, k4_pieces.cuh */
     const uint32_t dpiece = dpiece_bytes();
     const size_t   fixed = kCounterBytes + order_bytes(n_streams);
+    uint32_t      *jump_S = nullptr;
+    if (jump_span != 0) {
+        const size_t sbytes = align_up(static_cast<size_t>(jump_span) * sizeof(uint32_t), 256);
+        if (scratch_bytes > fixed + 4096 + sbytes) {
+            scratch_bytes -= sbytes;
+            jump_S = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(scratch) + scratch_bytes);
+        }
+    }
     if (dpiece != 0 && hist_len == nullptr && n_streams <= kCutStreamsMaxDecode && scratch_bytes > fixed + 4096) {
         /* as many table entries as the scratch holds (dpiece_table_bytes is linear in them) */
         const size_t   per_piece = lzs::dpiece_table_bytes(1, dpiece) - lzs::dpiece_table_bytes(0, dpiece);
@@ -601,7 +690,7 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
         const uint32_t cap = fit > 0x00FFFFFFull ? 0x00FFFFFFu : static_cast<uint32_t>(fit);
         if (cap >= 2u * n_streams + 16u && fixed + lzs::dpiece_table_bytes(cap, dpiece) <= scratch_bytes)
             return decompress_pieces(in, in_off, in_len, out, out_off, out_cap, out_len, status, n_streams, dpiece, cap,
-                                     static_cast<uint8_t *>(scratch) + fixed, st, d);
+                                     static_cast<uint8_t *>(scratch) + fixed, st, d, jump_S, jump_span, 0);
     }
     /* launch order: streams of similar density together, the fastest kind last (k4_decode.cuh);
      * needs scratch for one index per stream, otherwise the streams go in index order */
@@ -619,6 +708,9 @@ int lzs_b200_decompress_flows_batch_device(const uint8_t *in, const uint64_t *in
                    n_streams, st, d);
     return rc;
 }
+}  // namespace
+
+extern "C" {
 
 int lzs_b200_corpus_fill_device(uint8_t *dst, uint64_t stride, uint32_t stream_len, uint64_t first_index,
                                 uint64_t n, uint64_t seed, int kind, void *stream)
@@ -1042,7 +1134,13 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
      * slices, whose streams would each be decoded by one group of lanes */
     const bool    long_decode = decompress && dpiece_bytes() != 0 && n <= kCutStreamsMaxDecode &&
                              static_cast<uint64_t>(n) * 2u * dpiece_bytes() <= in_span;
-    const size_t  scratch = decompress ? (long_decode ? lzs_b200_decompress_scratch_bytes_long(in_span, n)
+    /* a handful of them: pointer doubling instead of the replay (4 bytes of scratch per byte of output) */
+    /* (one stream cannot make more than 30 bytes per byte: 15 per continuation nibble) */
+    const uint64_t jump_need = n == 1 && out_span > 30ull * in_span + 64u ? 30ull * in_span + 64u : out_span;
+    const uint32_t jump_span = long_decode && n <= jump_streams_max() && jump_need >= (1u << 20) && jump_need <= (1ull << 31)
+                                   ? static_cast<uint32_t>(jump_need) : 0u;
+    const size_t  scratch = decompress ? (long_decode ? lzs_b200_decompress_scratch_bytes_long(in_span, n) +
+                                                            align_up(static_cast<size_t>(jump_span) * 4u, 256) + 4096
                                                       : lzs_b200_decompress_scratch_bytes_for(n))
                                        : lzs_b200_compress_scratch_bytes(in_span);
     /* A decoder writes every output byte exactly once and reads none back (its history is in shared
@@ -1166,8 +1264,8 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
 
     if (in_span) CUDA_TRY(cudaMemcpyAsync(d_in, in, in_span, cudaMemcpyHostToDevice, st));
     if (decompress)
-        rc = lzs_b200_decompress_batch_device(d_in, d_inoff, d_inlen, d_out, d_outoff, d_outcap, d_outlen, n,
-                                              p.buf[S_SCRATCH], p.cap[S_SCRATCH], st);
+        rc = decompress_impl(d_in, d_inoff, d_inlen, d_out, d_outoff, d_outcap, nullptr, d_outlen, nullptr, n,
+                             p.buf[S_SCRATCH], scratch, st, jump_span);
     else
         rc = lzs_b200_compress_batch_device(d_in, d_inoff, d_inlen, in_span, d_out, d_outoff, d_outcap, d_outlen, n,
                                             p.buf[S_SCRATCH], p.cap[S_SCRATCH], st);

@@ -87,6 +87,10 @@ def lib():
     L.lzs_b200_set_decode_piece_bytes.argtypes = [ctypes.c_uint32]
     L.lzs_b200_decompress_scratch_bytes_long.restype = ctypes.c_size_t
     L.lzs_b200_decompress_scratch_bytes_long.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
+    L.lzs_b200_decompress_long_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_uint64, vp, vp, ctypes.c_uint32, vp,
+                                                        ctypes.c_size_t, vp]
+    L.lzs_b200_decompress_scratch_bytes_jump.restype = ctypes.c_size_t
+    L.lzs_b200_decompress_scratch_bytes_jump.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
     L.lzs_b200_pack_streams_device.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
     L.lzs_b200_pack_streams_peers_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
     L.lzs_b200_pack_streams_multicast_device.argtypes = [vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_uint32, vp]
@@ -308,6 +312,16 @@ class DeviceBatch:
             self.comp.data_ptr(), self.comp_off.data_ptr(), self.comp_len.data_ptr(),
             self.dec.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(), self.dec_len.data_ptr(),
             self.n, self.scratch.data_ptr(), self.scratch.numel(), self._stream()))
+
+    def decompress_jump(self):
+        """A handful of long streams: pointer doubling instead of the replay (lzs_b200_decompress_long_batch_device)."""
+        need = lib().lzs_b200_decompress_scratch_bytes_jump(self.n * self.comp_stride, self.total, self.n)
+        if self.scratch.numel() < need:
+            self.scratch = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        check(lib().lzs_b200_decompress_long_batch_device(
+            self.comp.data_ptr(), self.comp_off.data_ptr(), self.comp_len.data_ptr(),
+            self.dec.data_ptr(), self.raw_off.data_ptr(), self.raw_len.data_ptr(), self.total, self.dec_len.data_ptr(),
+            None, self.n, self.scratch.data_ptr(), self.scratch.numel(), self._stream()))
 
     def roundtrip_ok(self):
         t = self.torch

@@ -6,6 +6,8 @@
  */
 #define LZS_SIMT_EMU 1
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
 #include "../../lzs-compression_b200/csrc/k1_match.cuh"
 #include "../../lzs-compression_b200/csrc/k23_parse_pack.cuh"
 #include "../../lzs-compression_b200/csrc/k23_pieces.cuh"
@@ -126,18 +128,30 @@ extern "C" int emu_compress_pieces(const uint8_t *in, const uint64_t *in_off, co
  * dirty streams, pieces fix left open, table overflow. */
 extern "C" int emu_decode_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                                  const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
-                                 uint32_t piece, uint32_t cap, uint8_t *status, uint32_t *stats)
+                                 uint32_t piece, uint32_t cap, uint8_t *status, uint32_t *stats, uint32_t jump_span)
 {
     std::vector<uint32_t> mem(lzs::dpiece_table_bytes(cap, piece) / 4 + 16, 0xCDCDCDCDu);
+    std::vector<uint32_t> S(jump_span + 1, 0xCDCDCDCDu);
     const lzs::DPieceTable t = lzs::dpiece_table_at(mem.data(), cap, piece);
     const unsigned pgrid = (cap + 127) / 128, sgrid = (n + 3) / 4;
     simt::launch(dim3(1), dim3(1024), 0, [&] { lzs::k4p_plan(in_len, n, piece, t); });
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_spec(in, in_off, in_len, n, piece, t); });
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 0u, t); });
-    simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 1u, t); });
+    for (int rep = 0; rep < 3; rep++)
+        simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 1u, t); });
     simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_sweep(in, in_off, in_len, out_cap, out_len, status, n, piece, t); });
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_emit(in, in_off, in_len, out, out_off, n, piece, t); });
-    simt::launch(dim3(n), dim3(lzs::kDCopyThreads), 0, [&] { lzs::k4p_copy(out, out_off, out_len, n, t); });
+    if (jump_span) {
+        /* as decompress_pieces() does for a handful of streams: pointer doubling instead of the replay */
+        uint32_t *flags = t.count + 8;
+        simt::launch(dim3(3), dim3(256), 0, [&] { lzs::k4j_init(S.data(), jump_span, flags); });
+        simt::launch(dim3((cap + 3) / 4), dim3(128), 0, [&] { lzs::k4j_fill(out_off, 0, n, S.data(), t); });
+        for (int r = 0; r < lzs::kJumpRounds; r++)
+            simt::launch(dim3(3), dim3(256), 0, [&] { lzs::k4j_jump(S.data(), jump_span, flags, static_cast<uint32_t>(r)); });
+        simt::launch(dim3(3), dim3(256), 0, [&] { lzs::k4j_gather(out, 0, S.data(), jump_span); });
+    } else {
+        simt::launch(dim3(n), dim3(lzs::kDCopyThreads), 0, [&] { lzs::k4p_copy(out, out_off, out_len, n, t); });
+    }
     simt::launch(dim3((n + 127) / 128), dim3(128), 0, [&] { lzs::k4p_dirty_list(n, t); });
     simt::launch(dim3(2), dim3(lzs::kDecThreads), lzs::k4_smem_bytes<8>(), [&] {
         lzs::k4_decode<8>(in, in_off, in_len, out, out_off, out_cap, out_len, n, &t.count[3], status, t.dirty_list, nullptr,
@@ -149,6 +163,20 @@ extern "C" int emu_decode_pieces(const uint8_t *in, const uint64_t *in_off, cons
         stats[2] = 0;
         for (uint32_t i = 0; i < t.count[0]; i++) stats[2] += t.fix_status[i] == lzs::kDStOpen;
         stats[3] = t.count[1];
+        /* batches of 32 pieces the sweep can take at once (its chain condition), of all batches */
+        if (getenv("EMU_DBG_SWEEP")) {
+            unsigned all = 0, fast = 0;
+            for (uint32_t s2 = 0; s2 < n; s2++) {
+                for (uint32_t k0 = t.first[s2]; k0 < t.first[s2 + 1]; k0 += 32) {
+                    bool ok = k0 != t.first[s2];
+                    for (uint32_t k = k0; k < k0 + 32 && k < t.first[s2 + 1] && ok; k++)
+                        ok = t.fix_status[k] == lzs::kDStOk && t.fix_entry[k] == t.fix_exit[k - 1];
+                    all++;
+                    fast += ok;
+                }
+            }
+            fprintf(stderr, "sweep batches %u chained %u\n", all, fast);
+        }
     }
     return 0;
 }

@@ -611,7 +611,7 @@ def test_long_streams_decoder_small_pieces(B):
         db.compress()
         before = B.lib().lzs_b200_kernel_launches()
         db.decompress()
-        assert B.lib().lzs_b200_kernel_launches() - before == 9   # plan, spec, fix x2, sweep, emit, copy, dirty list, k4_decode for the dirty
+        assert B.lib().lzs_b200_kernel_launches() - before == 11  # plan, spec, fix x4, sweep, emit, copy, dirty list, k4_decode for the dirty
         torch.cuda.synchronize()
         assert db.roundtrip_ok()
     finally:
@@ -626,7 +626,7 @@ def test_long_streams_decoder_1mib_chunks(B, kind):
     db.compress()
     before = B.lib().lzs_b200_kernel_launches()
     db.decompress()
-    assert B.lib().lzs_b200_kernel_launches() - before == 9
+    assert B.lib().lzs_b200_kernel_launches() - before == 11
     torch.cuda.synchronize()
     assert db.roundtrip_ok()
 
@@ -714,3 +714,18 @@ def test_long_streams_structured_fuzz_both_directions(B):
         B.set_decode_piece_bytes(2048)
     for i, (s, c, g) in enumerate(zip(streams, caps, back)):
         assert g == ref.decompress(s, c), i
+
+
+@pytest.mark.parametrize("chunk_mib,kind", [(16, "mixed"), (4, "text"), (32, "random")])
+def test_long_streams_decoder_by_pointer_doubling(B, chunk_mib, kind):
+    """lzs_b200_decompress_long_batch_device: a handful of long streams, every byte fetched from the literal it
+    is a copy of (csrc/k4_pieces.cuh, k4j_*); the round trip, and the lengths."""
+    import torch
+    db = B.DeviceBatch(96 << 20, chunk_mib << 20)
+    db.fill({"mixed": B.CORPUS_MIXED, "text": B.CORPUS_TEXT, "random": B.CORPUS_RANDOM}[kind], 0x5EED0000 + 52)
+    db.compress()
+    before = B.lib().lzs_b200_kernel_launches()
+    db.decompress_jump()
+    assert B.lib().lzs_b200_kernel_launches() - before == 8 + 3 + 32 + 2   # pieces, init/fill/gather, 32 doubling rounds, dirty list + k4_decode
+    torch.cuda.synchronize()
+    assert db.roundtrip_ok()

@@ -75,7 +75,11 @@ def test_pieces_table_too_small_produces_nothing():
 
 # ---------------------------------------------------------------- the decoder for long streams (csrc/k4_pieces.cuh)
 
+JUMP = [False]          # the same checks with the copies resolved by pointer doubling (the host calls' way for a handful of streams)
+
+
 def _decode_check(streams, caps, piece, **kw):
+    kw.setdefault("jump", JUMP[0])
     """Outputs and stop reasons must be the oracle's (= the reference's, tests/test_oracle.py) whether a
     stream is finished by the piece passes or handed to k4_decode as dirty."""
     o = helpers.oracle()
@@ -193,3 +197,16 @@ def test_pieces_structured_fuzz_decoder():
                 streams.append(c + rng.integers(0, 256, 7, dtype=np.uint8).tobytes()); caps.append(len(d) + 9)
         _decode_check(streams, caps, int(rng.integers(16, 300)), lead=int(rng.integers(0, 4)), align=4,
                       out_lead=int(rng.integers(0, 8)))
+
+
+def test_decode_pieces_pointer_doubling_instead_of_replay():
+    """k4j_*: every byte finds the literal it is a copy of by pointer doubling.  The decoder's tests again,
+    with that in place of the replay."""
+    JUMP[0] = True
+    try:
+        test_decode_pieces_clean_streams(50)
+        test_decode_pieces_long_tokens_and_unaligned()
+        test_decode_pieces_damaged_streams_and_short_outputs()
+        test_pieces_structured_fuzz_decoder()
+    finally:
+        JUMP[0] = False

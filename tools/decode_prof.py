@@ -11,6 +11,7 @@ ap.add_argument("--mib", type=int, default=1024)
 ap.add_argument("--chunk", type=int, default=1 << 20)
 ap.add_argument("--dpiece", type=int, default=2048)
 ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--jump", action="store_true", help="pointer doubling instead of the replay")
 a = ap.parse_args()
 total = a.mib << 20
 B.set_decode_piece_bytes(a.dpiece)
@@ -20,8 +21,8 @@ db.compress()
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for it in range(a.iters):
-    ev[0].record(); db.decompress(); ev[1].record()
+    ev[0].record(); (db.decompress_jump() if a.jump else db.decompress()); ev[1].record()
     torch.cuda.synchronize()
     t = ev[0].elapsed_time(ev[1])
-    print("chunk=%d dpiece=%d iter %d: decompress %.2f ms (%.1f GB/s)" % (a.chunk, a.dpiece, it, t, total / t / 1e6))
+    print(("jump " if a.jump else "") + "chunk=%d dpiece=%d iter %d: decompress %.2f ms (%.1f GB/s)" % (a.chunk, a.dpiece, it, t, total / t / 1e6))
 assert db.roundtrip_ok()

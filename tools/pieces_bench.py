@@ -86,10 +86,20 @@ def main():
                 ev[0].record(); db.decompress(); ev[1].record()
                 torch.cuda.synchronize()
                 best = min(best, ev[0].elapsed_time(ev[1]))
-            cut = (B.lib().lzs_b200_kernel_launches() - before) // iters == 9
+            cut = (B.lib().lzs_b200_kernel_launches() - before) // iters == 11
             assert db.roundtrip_ok(), "decode differs with pieces of %d" % dpiece
             row["dpiece_%d" % dpiece if dpiece else "uncut"] = {"ms": round(best, 2), "gbs": round(total / best / 1e6, 2), "cut": cut}
         B.set_decode_piece_bytes(2048)
+        if total // chunk <= 1024:
+            # a handful of streams: pointer doubling instead of the replay (lzs_b200_decompress_long_batch_device)
+            best = 1e30
+            for _ in range(3):
+                db.dec.zero_()
+                ev[0].record(); db.decompress_jump(); ev[1].record()
+                torch.cuda.synchronize()
+                best = min(best, ev[0].elapsed_time(ev[1]))
+            assert db.roundtrip_ok(), "decode by pointer doubling differs"
+            row["jump"] = {"ms": round(best, 2), "gbs": round(total / best / 1e6, 2)}
         del db
         torch.cuda.empty_cache()
         print(json.dumps(row), flush=True)
