@@ -12,7 +12,9 @@
  * independent chunks are what both the compressor and the decoder of the GPU take in parallel.
  * With `-s` (or a chunk size of at least the file size) the output is the single stream the
  * reference's lzs-compress writes, byte for byte; the library compresses it in parallel all the
- * same (cut into pieces inside, csrc/k23_pieces.cuh), but nobody can DEcode one stream in parallel.
+ * same (cut into pieces inside, csrc/k23_pieces.cuh).  (`d` without an index goes through the
+ * incremental calls, which are serial; lzs_decompress on the whole buffer is the fast way to decode one
+ * stream: csrc/k4_pieces.cuh.)
  *
  * Finding the stream starts again needs a scan of the whole bit stream, so `c -x` also writes a
  * small index (one (uncompressed, compressed) length pair per chunk) and `d -x` uses it to decode

@@ -29,3 +29,5 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k4p_
     python tools/decode_prof.py --mib 256 --chunk 1048576 --iters 1 > /dev/null 2>&1
 timeout 600 compute-sanitizer --tool memcheck python tools/sanitize.py 2>&1 | tail -7 > gpurun_out/${R}_memcheck.txt; tail -3 gpurun_out/${R}_memcheck.txt
 timeout 600 compute-sanitizer --tool synccheck python tools/sanitize.py 2>&1 | tail -3 > gpurun_out/${R}_synccheck.txt; tail -2 gpurun_out/${R}_synccheck.txt
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${R}_decode_jump_launches.csv \
+    python tools/decode_prof.py --mib 1024 --chunk 268435456 --iters 1 --jump > /dev/null 2>&1
