@@ -11,4 +11,7 @@ comp = [o.compress(d) for d in data]
 B.set_decode_piece_bytes(256)
 got = B.decompress_streams(comp, [len(d) for d in data])
 assert got == data
+B.set_decode_piece_bytes(2048)
+big = [helpers.corpus(kind, 1, 600000, first_index=5).tobytes() for kind in (helpers.CORPUS_TEXT, helpers.CORPUS_MIXED)]
+assert B.decompress_streams([o.compress(d) for d in big], [len(d) for d in big]) == big      # pointer doubling (out_span >= 1 MiB)
 print("racecheck workload ok")

@@ -87,3 +87,14 @@ got = B.decompress_streams(mixed_bag, bag_caps)
 B.set_decode_piece_bytes(2048)
 assert got == [o.decompress(s, c) for s, c in zip(mixed_bag, bag_caps)]
 print("sanitize workload (decoder pieces) ok")
+# a handful of long streams through the host call: the copies resolved by pointer doubling (k4j_*), one of them damaged
+big3 = [helpers.corpus(kind, 1, 420000, first_index=9).tobytes() for kind in (helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_MIXED)]
+big3.append(b"\0" * 300000 + b"ab" * 100000)
+c3 = [o.compress(d) for d in big3]
+c3.append(c3[0][:len(c3[0]) // 2])
+caps3 = [len(d) for d in big3] + [len(big3[0])]
+B.set_decode_piece_bytes(512)
+got = B.decompress_streams(c3, caps3)
+B.set_decode_piece_bytes(2048)
+assert got == [o.decompress(s, c) for s, c in zip(c3, caps3)]
+print("sanitize workload (pointer doubling) ok")
