@@ -872,6 +872,7 @@ struct HostPath {
         buf[slot] = nullptr;
         cap[slot] = 0;
         cudaError_t e = cudaMalloc(&buf[slot], bytes);
+        if (e != cudaSuccess) cudaGetLastError();        /* not sticky; a caller may go on with a smaller request */
         if (e != cudaSuccess)
             return fail(e == cudaErrorNoDevice ? LZS_B200_ENODEVICE : LZS_B200_ENOMEM,
                         "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -1137,12 +1138,15 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     /* a handful of them: pointer doubling instead of the replay (4 bytes of scratch per byte of output) */
     /* (one stream cannot make more than 30 bytes per byte: 15 per continuation nibble) */
     const uint64_t jump_need = n == 1 && out_span > 30ull * in_span + 64u ? 30ull * in_span + 64u : out_span;
-    const uint32_t jump_span = long_decode && n <= jump_streams_max() && jump_need >= (1u << 20) && jump_need <= (1ull << 31)
-                                   ? static_cast<uint32_t>(jump_need) : 0u;
-    const size_t  scratch = decompress ? (long_decode ? lzs_b200_decompress_scratch_bytes_long(in_span, n) +
-                                                            align_up(static_cast<size_t>(jump_span) * 4u, 256) + 4096
-                                                      : lzs_b200_decompress_scratch_bytes_for(n))
-                                       : lzs_b200_compress_scratch_bytes(in_span);
+    uint32_t jump_span = long_decode && n <= jump_streams_max() && jump_need >= (1u << 20) && jump_need <= (1ull << 31)
+                             ? static_cast<uint32_t>(jump_need) : 0u;
+    auto scratch_for = [&](uint32_t span) {
+        return decompress ? (long_decode ? lzs_b200_decompress_scratch_bytes_long(in_span, n) +
+                                               (span ? align_up(static_cast<size_t>(span) * 4u, 256) + 4096 : 0)
+                                         : lzs_b200_decompress_scratch_bytes_for(n))
+                          : lzs_b200_compress_scratch_bytes(in_span);
+    };
+    size_t scratch = scratch_for(jump_span);
     /* A decoder writes every output byte exactly once and reads none back (its history is in shared
      * memory), so when the caller's output buffer is pinned and device mapped it CAN decode straight
      * into it over PCIe (option, off by default: see mapped_host_range). */
@@ -1155,7 +1159,12 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     if ((rc = p.reserve(S_OUTOFF, n * sizeof(uint64_t)))) return rc;
     if ((rc = p.reserve(S_OUTCAP, n * sizeof(uint32_t)))) return rc;
     if ((rc = p.reserve(S_OUTLEN, n * sizeof(uint32_t)))) return rc;
-    if ((rc = p.reserve(S_SCRATCH, scratch))) return rc;
+    if ((rc = p.reserve(S_SCRATCH, scratch))) {
+        if (jump_span == 0) return rc;
+        jump_span = 0;                      /* no room for a pointer per output byte: the replay instead */
+        scratch = scratch_for(0);
+        if ((rc = p.reserve(S_SCRATCH, scratch))) return rc;
+    }
 
     uint8_t  *d_in = static_cast<uint8_t *>(p.buf[S_IN]);
     uint8_t  *d_out = direct_out ? direct_out : static_cast<uint8_t *>(p.buf[S_OUT]);
