@@ -162,6 +162,15 @@ int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, co
                                    const uint32_t *out_cap, uint32_t *out_len, uint64_t out_span,
                                    uint32_t n_streams);
 
+/* The same, and in_used[s] = bytes of stream s read up to and including its end marker: what a caller
+ * needs to walk a buffer of several streams laid end to end without an index (the reference's file
+ * format, c/src/utils/lzs-decompress.c:75-118).  0xFFFFFFFF where that is not known (short streams, streams
+ * that are not clean, outputs that did not fit): decode those the slow way. */
+int lzs_b200_decompress_used_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                        uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                        const uint32_t *out_cap, uint32_t *out_len, uint32_t *in_used,
+                                        uint64_t out_span, uint32_t n_streams);
+
 /* Packed variant of lzs_b200_compress_batch_host for streams given in increasing order (chunks of
  * a file, a packet table): the streams are written back to back, each starting at a multiple of
  * 16, and out_off[s] / out_len[s] are OUTPUTS.  Only compressed bytes travel back over PCIe, and

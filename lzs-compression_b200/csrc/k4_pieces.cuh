@@ -395,13 +395,14 @@ k4p_fix(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, con
 __global__ void __launch_bounds__(128)
 k4p_sweep(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, const uint32_t *__restrict__ in_len,
           const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ out_len, uint8_t *__restrict__ status,
-          uint32_t n_streams, uint32_t piece, DPieceTable t)
+          uint32_t n_streams, uint32_t piece, DPieceTable t, uint32_t *__restrict__ in_used = nullptr)
 {
     const uint32_t sid = blockIdx.x * 4u + (threadIdx.x >> 5);
     if (sid >= n_streams) return;
     const uint32_t lane = lane_id();
     if (t.count[1]) {                                    /* no table: everything to k4_decode */
         if (lane == 0) t.dirty[sid] = 1;
+        if (lane == 0 && in_used != nullptr) in_used[sid] = 0xFFFFFFFFu;
         return;
     }
     const BitSrc   s = bitsrc_open(in + in_off[sid], in_len[sid]);
@@ -497,6 +498,9 @@ k4p_sweep(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, c
     }
     /* (entries stored before `bad` was known are harmless: a dirty stream is decoded again) */
     if (lane == 0) {
+        /* bytes of the stream up to and including its end marker (e stands on it), for callers that
+         * walk a file of several streams; unknown for a stream that is not clean */
+        if (in_used != nullptr) in_used[sid] = (bad || !ended) ? 0xFFFFFFFFu : (e + 9u - s.first + 7u) >> 3;
         if (bad || !ended) {
             t.dirty[sid] = 1;
         } else {

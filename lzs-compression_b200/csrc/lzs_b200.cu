@@ -471,7 +471,7 @@ int launch_k4(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
 int decompress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                       const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint8_t *status,
                       uint32_t n_streams, uint32_t piece, uint32_t cap, void *table_mem, cudaStream_t st, DeviceInfo *d,
-                      uint32_t *jump_S = nullptr, uint32_t jump_span = 0, uint64_t jump_base = 0)
+                      uint32_t *jump_S = nullptr, uint32_t jump_span = 0, uint64_t jump_base = 0, uint32_t *in_used = nullptr)
 {
     const lzs::DPieceTable t = lzs::dpiece_table_at(table_mem, cap, piece);
     const unsigned pgrid = (cap + 127u) / 128u, sgrid = (n_streams + 3u) / 4u;
@@ -479,7 +479,7 @@ int decompress_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t 
     lzs::k4p_spec<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, t);
     lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 0u, t);
     for (int rep = 0; rep < fix_repairs(); rep++) lzs::k4p_fix<<<pgrid, 128, 0, st>>>(in, in_off, in_len, n_streams, piece, 1u, t);
-    lzs::k4p_sweep<<<sgrid, 128, 0, st>>>(in, in_off, in_len, out_cap, out_len, status, n_streams, piece, t);
+    lzs::k4p_sweep<<<sgrid, 128, 0, st>>>(in, in_off, in_len, out_cap, out_len, status, n_streams, piece, t, in_used);
     lzs::k4p_emit<<<pgrid, 128, 0, st>>>(in, in_off, in_len, out, out_off, n_streams, piece, t);
     g_launches += 5 + fix_repairs();
     if (jump_S != nullptr) {
@@ -508,7 +508,7 @@ namespace {
 int decompress_impl(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                     const uint64_t *out_off, const uint32_t *out_cap, const uint32_t *hist_len, uint32_t *out_len,
                     uint8_t *status, uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream,
-                    uint32_t jump_span);
+                    uint32_t jump_span, uint32_t *in_used = nullptr);
 }
 
 extern "C" {
@@ -659,7 +659,7 @@ namespace {
 int decompress_impl(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                     const uint64_t *out_off, const uint32_t *out_cap, const uint32_t *hist_len, uint32_t *out_len,
                     uint8_t *status, uint32_t n_streams, void *scratch, size_t scratch_bytes, void *stream,
-                    uint32_t jump_span)
+                    uint32_t jump_span, uint32_t *in_used)
 {
     if (n_streams == 0) return LZS_B200_OK;
     if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len)
@@ -690,7 +690,7 @@ int decompress_impl(const uint8_t *in, const uint64_t *in_off, const uint32_t *i
         const uint32_t cap = fit > 0x00FFFFFFull ? 0x00FFFFFFu : static_cast<uint32_t>(fit);
         if (cap >= 2u * n_streams + 16u && fixed + lzs::dpiece_table_bytes(cap, dpiece) <= scratch_bytes)
             return decompress_pieces(in, in_off, in_len, out, out_off, out_cap, out_len, status, n_streams, dpiece, cap,
-                                     static_cast<uint8_t *>(scratch) + fixed, st, d, jump_S, jump_span, 0);
+                                     static_cast<uint8_t *>(scratch) + fixed, st, d, jump_S, jump_span, 0, in_used);
     }
     /* launch order: streams of similar density together, the fastest kind last (k4_decode.cuh);
      * needs scratch for one index per stream, otherwise the streams go in index order */
@@ -1117,7 +1117,7 @@ std::vector<uint32_t> plan_slices(const uint32_t *weight, uint32_t n, uint64_t t
 
 int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
                    uint64_t in_span, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
-                   uint32_t *out_len, uint64_t out_span, uint32_t n)
+                   uint32_t *out_len, uint64_t out_span, uint32_t n, uint32_t *in_used = nullptr)
 {
     if (n == 0) return LZS_B200_OK;
     if (!in_off || !in_len || !out_off || !out_cap || !out_len || (!in && in_span) || (!out && out_span))
@@ -1183,7 +1183,7 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
      * overlap: slice k uploads and computes on work[k % 8] (the decoder needs several
      * slices resident at once to fill the GPU), finished slices are downloaded on `down`, and
      * only the bytes a slice really produced come back. */
-    bool ordered = n > 8 && !long_decode;
+    bool ordered = n > 8 && !long_decode && in_used == nullptr;
     for (uint32_t s2 = 1; s2 < n && ordered; s2++)
         ordered = in_off[s2] >= in_off[s2 - 1] + in_len[s2 - 1] && out_off[s2] >= out_off[s2 - 1] + out_cap[s2 - 1];
     if (ordered) {
@@ -1272,14 +1272,21 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     }
 
     if (in_span) CUDA_TRY(cudaMemcpyAsync(d_in, in, in_span, cudaMemcpyHostToDevice, st));
+    uint32_t *d_used = nullptr;
+    if (decompress && in_used != nullptr) {             /* bytes every stream took up to its end marker (unknown: all ones) */
+        if ((rc = p.reserve(S_COUNTERS, static_cast<size_t>(n) * sizeof(uint32_t)))) return rc;
+        d_used = static_cast<uint32_t *>(p.buf[S_COUNTERS]);
+        CUDA_TRY(cudaMemsetAsync(d_used, 0xFF, static_cast<size_t>(n) * sizeof(uint32_t), st));
+    }
     if (decompress)
         rc = decompress_impl(d_in, d_inoff, d_inlen, d_out, d_outoff, d_outcap, nullptr, d_outlen, nullptr, n,
-                             p.buf[S_SCRATCH], scratch, st, jump_span);
+                             p.buf[S_SCRATCH], scratch, st, jump_span, d_used);
     else
         rc = lzs_b200_compress_batch_device(d_in, d_inoff, d_inlen, in_span, d_out, d_outoff, d_outcap, d_outlen, n,
                                             p.buf[S_SCRATCH], p.cap[S_SCRATCH], st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_len, d_outlen, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (d_used) CUDA_TRY(cudaMemcpyAsync(in_used, d_used, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     /* only what was produced comes back, and nothing outside the slots is touched */
     if (!direct_out && (rc = download_streams(p, out, d_out, out_off, out_cap, out_len, 0, n, st, nullptr))) return rc;
@@ -1498,6 +1505,19 @@ int lzs_b200_compress_packed_host(const uint8_t *in, const uint64_t *in_off, con
                                   uint32_t *out_len, uint32_t n_streams, uint64_t *out_used)
 {
     return run_compress_packed(in, in_off, in_len, in_span, out, out_capacity, out_off, out_len, n_streams, out_used);
+}
+
+/* lzs_b200_decompress_batch_host that also says how many bytes of every stream were read up to and including its
+ * end marker -- what a caller needs to walk a buffer of several streams laid end to end without an index.
+ * 0xFFFFFFFF where that is not known (the stream is short, not clean, or its output did not fit). */
+int lzs_b200_decompress_used_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+                                        uint64_t in_span, uint8_t *out, const uint64_t *out_off,
+                                        const uint32_t *out_cap, uint32_t *out_len, uint32_t *in_used, uint64_t out_span,
+                                        uint32_t n_streams)
+{
+    if (!in_used) return fail(LZS_B200_EINVAL, "null pointer");
+    for (uint32_t s = 0; s < n_streams; s++) in_used[s] = 0xFFFFFFFFu;
+    return run_host_batch(true, in, in_off, in_len, in_span, out, out_off, out_cap, out_len, out_span, n_streams, in_used);
 }
 
 int lzs_b200_decompress_batch_host(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,

@@ -12,9 +12,8 @@
  * independent chunks are what both the compressor and the decoder of the GPU take in parallel.
  * With `-s` (or a chunk size of at least the file size) the output is the single stream the
  * reference's lzs-compress writes, byte for byte; the library compresses it in parallel all the
- * same (cut into pieces inside, csrc/k23_pieces.cuh).  (`d` without an index goes through the
- * incremental calls, which are serial; lzs_decompress on the whole buffer is the fast way to decode one
- * stream: csrc/k4_pieces.cuh.)
+ * same (cut into pieces inside, csrc/k23_pieces.cuh), and `d` decodes long streams of an index-less file in
+ * parallel inside each stream (csrc/k4_pieces.cuh), walking from end marker to end marker.
  *
  * Finding the stream starts again needs a scan of the whole bit stream, so `c -x` also writes a
  * small index (one (uncompressed, compressed) length pair per chunk) and `d -x` uses it to decode
@@ -157,14 +156,45 @@ int decompress_with_index(const std::vector<uint8_t> &in, const std::vector<uint
 }
 
 /* the reference CLI's loop (c/src/utils/lzs-decompress.c:75-118) over the same incremental call */
+/* A file without an index whose streams are LONG (the reference's own lzs-compress writes ONE): every
+ * stream is decoded by one batch-class call (token starts found in parallel, copies resolved by pointer
+ * doubling: csrc/k4_pieces.cuh), which also says where the stream's end marker is, so the next stream
+ * can be found.  Returns the bytes of `in` that were decoded this way (0: none); whatever is left --
+ * short streams, a damaged tail -- goes through the incremental calls like the reference's CLI. */
+size_t decompress_long_streams(const std::vector<uint8_t> &in, std::vector<uint8_t> &out)
+{
+    const size_t kWorth = 1u << 20;                  /* below this a stream is not worth a call of its own */
+    size_t       pos = 0;
+    while (in.size() - pos >= kWorth) {
+        const uint64_t in_off = 0, out_off = 0;
+        const uint64_t rest = in.size() - pos;
+        const uint32_t in_len = static_cast<uint32_t>(rest < 0x1FFFFF00ull ? rest : 0x1FFFFF00ull);
+        /* one stream cannot make more than 30 bytes per byte; 1 GiB per call at most */
+        const uint64_t want = 30ull * in_len + 64u;
+        const uint32_t cap = static_cast<uint32_t>(want < (1ull << 30) ? want : (1ull << 30));
+        std::vector<uint8_t> buf(static_cast<size_t>(cap) + 64u);
+        std::vector<uint8_t> src(in.begin() + pos, in.begin() + pos + in_len);
+        src.resize(src.size() + 16);
+        uint32_t out_len = 0, used = 0xFFFFFFFFu;
+        if (lzs_b200_decompress_used_batch_host(src.data(), &in_off, &in_len, in_len, buf.data(), &out_off, &cap, &out_len,
+                                                &used, cap, 1) != LZS_B200_OK)
+            break;
+        if (used == 0xFFFFFFFFu || used < kWorth) break;   /* not clean, did not fit, or short streams: the slow way from here */
+        out.insert(out.end(), buf.begin(), buf.begin() + out_len);
+        pos += used;
+    }
+    return pos;
+}
+
 int decompress_stream(const std::vector<uint8_t> &in, const char *out_path)
 {
     LzsDecompressParameters_t p;
     lzs_decompress_init(&p);
     std::vector<uint8_t> out;
+    const size_t         done = decompress_long_streams(in, out);
     std::vector<uint8_t> buf(1u << 20);
-    p.inPtr = in.data();
-    p.inLength = in.size();
+    p.inPtr = in.data() + done;
+    p.inLength = in.size() - done;
     for (;;) {
         if (p.inLength == 0 && (p.status & LZS_D_STATUS_INPUT_STARVED) != 0) break;    /* as the reference CLI */
         p.outPtr = buf.data();

@@ -141,7 +141,8 @@ def compress_pieces(streams, piece, caps=None, grid=1, align=16, lead=0, out_lea
     return _collect(dst, out_off, caps, out_len, "packer"), stats
 
 
-def decode_pieces(streams, caps, piece, align=16, lead=0, out_lead=0, cap_entries=None, with_status=False, jump=False):
+def decode_pieces(streams, caps, piece, align=16, lead=0, out_lead=0, cap_entries=None, with_status=False, jump=False,
+                  in_used=None):
     """The decoder for long streams (csrc/k4_pieces.cuh): compressed streams cut into pieces of `piece`
     bytes, dirty streams finished by k4_decode.  Returns (outputs, stats[, status]) with stats = [pieces,
     dirty streams, pieces fix left open, table overflow]."""
@@ -154,10 +155,10 @@ def decode_pieces(streams, caps, piece, align=16, lead=0, out_lead=0, cap_entrie
         cap_entries = sum(max(1, -(-len(s) // piece)) for s in streams) + len(streams) + 3
     L = lib()
     L.emu_decode_pieces.argtypes = [c_u8p, c_u64p, c_u32p, c_u8p, c_u64p, c_u32p, c_u32p, ctypes.c_uint32,
-                                    ctypes.c_uint32, ctypes.c_uint32, c_u8p, c_u32p, ctypes.c_uint32]
+                                    ctypes.c_uint32, ctypes.c_uint32, c_u8p, c_u32p, ctypes.c_uint32, c_u32p]
     L.emu_decode_pieces(_ptr(src), _ptr(in_off, c_u64p), _ptr(in_len, c_u32p), _ptr(dst), _ptr(out_off, c_u64p),
                         _ptr(out_cap, c_u32p), _ptr(out_len, c_u32p), len(streams), piece, cap_entries, _ptr(status),
-                        _ptr(stats, c_u32p), len(dst) if jump else 0)
+                        _ptr(stats, c_u32p), len(dst) if jump else 0, _ptr(in_used, c_u32p) if in_used is not None else None)
     got = _collect(dst, out_off, caps, out_len, "decoder")
     return (got, stats, status[:len(streams)]) if with_status else (got, stats)
 

@@ -128,7 +128,7 @@ extern "C" int emu_compress_pieces(const uint8_t *in, const uint64_t *in_off, co
  * dirty streams, pieces fix left open, table overflow. */
 extern "C" int emu_decode_pieces(const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint8_t *out,
                                  const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, uint32_t n,
-                                 uint32_t piece, uint32_t cap, uint8_t *status, uint32_t *stats, uint32_t jump_span)
+                                 uint32_t piece, uint32_t cap, uint8_t *status, uint32_t *stats, uint32_t jump_span, uint32_t *in_used)
 {
     std::vector<uint32_t> mem(lzs::dpiece_table_bytes(cap, piece) / 4 + 16, 0xCDCDCDCDu);
     std::vector<uint32_t> S(jump_span + 1, 0xCDCDCDCDu);
@@ -139,7 +139,7 @@ extern "C" int emu_decode_pieces(const uint8_t *in, const uint64_t *in_off, cons
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 0u, t); });
     for (int rep = 0; rep < 3; rep++)
         simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_fix(in, in_off, in_len, n, piece, 1u, t); });
-    simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_sweep(in, in_off, in_len, out_cap, out_len, status, n, piece, t); });
+    simt::launch(dim3(sgrid), dim3(128), 0, [&] { lzs::k4p_sweep(in, in_off, in_len, out_cap, out_len, status, n, piece, t, in_used); });
     simt::launch(dim3(pgrid), dim3(128), 0, [&] { lzs::k4p_emit(in, in_off, in_len, out, out_off, n, piece, t); });
     if (jump_span) {
         /* as decompress_pieces() does for a handful of streams: pointer doubling instead of the replay */

@@ -126,3 +126,25 @@ def test_file_cli_single_stream_of_a_large_file_equals_reference_compressor(tmp_
     assert ours.read_bytes() == theirs.read_bytes()
     _run(_bin("ref-lzs-decompress"), str(ours), str(back))
     assert back.read_bytes() == data
+
+
+def test_file_cli_decodes_long_streams_of_an_index_less_file_in_parallel(tmp_path):
+    """`lzs-b200 d` on the reference's own files: ONE long stream (what lzs-compress writes), and two long
+    streams followed by short ones laid end to end.  Long streams are decoded by one batch-class call each
+    (csrc/k4_pieces.cuh), found by the end marker's position; the rest goes the reference CLI's way."""
+    a = b"".join(helpers.corpus(kind, 1, 2 << 20, seed=0x5EED0000 + 40 + kind).tobytes()
+                 for kind in (helpers.CORPUS_TEXT, helpers.CORPUS_BINARY, helpers.CORPUS_MIXED)) + bytes(1 << 20)
+    b = helpers.corpus(helpers.CORPUS_MIXED, 1, 5 << 20, seed=0x5EED0000 + 44).tobytes()
+    small = [helpers.corpus(helpers.CORPUS_TEXT, 1, 3000 + i, seed=0x5EED0000 + 45 + i).tobytes() for i in range(3)]
+    for tag, parts in (("one", [a]), ("several", [a, b] + small)):
+        comp = tmp_path / (tag + ".lzs")
+        blob = b""
+        for i, part in enumerate(parts):
+            src, one = tmp_path / ("%s_%d.bin" % (tag, i)), tmp_path / ("%s_%d.lzs" % (tag, i))
+            src.write_bytes(part)
+            _run(_bin("ref-lzs-compress"), str(src), str(one))
+            blob += one.read_bytes()
+        comp.write_bytes(blob)
+        back = tmp_path / (tag + ".back")
+        _run(_cli(), "d", str(comp), str(back))
+        assert back.read_bytes() == b"".join(parts), tag

@@ -210,3 +210,18 @@ def test_decode_pieces_pointer_doubling_instead_of_replay():
         test_pieces_structured_fuzz_decoder()
     finally:
         JUMP[0] = False
+
+
+def test_decode_pieces_report_where_the_end_marker_is():
+    """in_used: bytes of a stream up to and including its end marker (what walks a file of several streams laid
+    end to end); unknown (all ones) for streams that are not clean."""
+    o = helpers.oracle()
+    data = [helpers.corpus(helpers.CORPUS_MIXED, 1, 5000 + 13 * i, first_index=i).tobytes() for i in range(4)]
+    comp = [o.compress(d) for d in data]
+    streams = [comp[0], comp[1] + b"\x12\x34\x56" * 40, comp[2] + comp[3], comp[3][:len(comp[3]) // 2]]
+    caps = [len(data[0]), len(data[1]) + 7, len(data[2]) + 100, len(data[3])]
+    used = np.zeros(4, dtype=np.uint32)
+    got, _ = emu.decode_pieces(streams, caps, 40, in_used=used, lead=1, align=4)
+    assert got[:3] == data[:3]
+    assert list(used[:3]) == [len(comp[0]), len(comp[1]), len(comp[2])]
+    assert used[3] == 0xFFFFFFFF
