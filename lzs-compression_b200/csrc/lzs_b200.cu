@@ -158,6 +158,18 @@ uint32_t dpiece_bytes()
     return static_cast<uint32_t>(v);
 }
 constexpr uint32_t kCutStreamsMaxDecode = 4096;
+/* ... when the output is at least this long (LZS_B200_JUMP_MIN) */
+uint64_t jump_bytes_min()
+{
+    static long long v = -1;
+    if (v < 0) {
+        const char *e = getenv("LZS_B200_JUMP_MIN");
+        v = e ? atoll(e) : 16384;    /* measured, one lzs_decompress call: 32 KiB .. 512 KiB take 1.2 .. 2.4 ms this way, 1.3 .. 5.3 ms
+                                        with the replay, 2.2 .. 34 ms with one group of lanes (tools/small_calls_probe.py) */
+        if (v < 4096) v = 4096;
+    }
+    return static_cast<uint64_t>(v);
+}
 /* repair passes of k4p_fix after the first (LZS_B200_FIX_REPAIRS): a piece whose guess never joined its true
  * orbit gives the NEXT piece a wrong entry, and runs of such pieces are repaired one piece per pass */
 int fix_repairs()
@@ -1138,7 +1150,7 @@ int run_host_batch(bool decompress, const uint8_t *in, const uint64_t *in_off, c
     /* a handful of them: pointer doubling instead of the replay (4 bytes of scratch per byte of output) */
     /* (one stream cannot make more than 30 bytes per byte: 15 per continuation nibble) */
     const uint64_t jump_need = n == 1 && out_span > 30ull * in_span + 64u ? 30ull * in_span + 64u : out_span;
-    uint32_t jump_span = long_decode && n <= jump_streams_max() && jump_need >= (1u << 20) && jump_need <= (1ull << 31)
+    uint32_t jump_span = long_decode && n <= jump_streams_max() && jump_need >= jump_bytes_min() && jump_need <= (1ull << 31)
                              ? static_cast<uint32_t>(jump_need) : 0u;
     auto scratch_for = [&](uint32_t span) {
         return decompress ? (long_decode ? lzs_b200_decompress_scratch_bytes_long(in_span, n) +
